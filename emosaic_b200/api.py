@@ -1,0 +1,415 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+Names, argument meaning and error behaviour follow the reference (paths under the reference
+root): ``analyse`` (src/mosaic/analysis.rs:5), ``get_img_colors`` (analysis.rs:23), ``Tile`` /
+``Tile.coords`` (tiles/tile.rs), ``flipped_coords`` (tiles/utils.rs:18), ``TileSet`` /
+``build_kiddo`` / ``get_tile`` / ``get_image`` (tiles/tileset.rs), ``render_nto1``
+(rendering.rs:124) and the tint block (main.rs:447-478).  Where the reference panics or exits,
+these raise ``EmosaicError`` (status code + the reference's message).
+
+All compute goes through ``libemosaic_cuda.so``; numpy is only used to hold host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import EmosaicError, check
+
+EMO_ERR_ARG = -1
+EMO_ERR_UNSUPPORTED = -5
+
+
+def _u8(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _isqrt_exact(N: int) -> int:
+    d = math.isqrt(N)
+    if d * d != N or N < 1:
+        raise EmosaicError(EMO_ERR_ARG, f"N={N} is not a square number of cells")
+    return d
+
+
+class Context:
+    """One per GPU (one process per GPU under torchrun).  Wraps ``emo_ctx``."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.emo_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+        self.N = 0
+        self.dim = 0
+        self.ts = 0
+        self.T = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.emo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing -------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None):
+        check(self._lib.emo_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        check(self._lib.emo_sync(self._h))
+
+    def device_info(self):
+        name = C.create_string_buffer(256)
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.emo_device_info(self._h, name, 256, C.byref(sm), C.byref(ma), C.byref(mi)))
+        return {"name": name.value.decode(), "sm_count": sm.value, "cc": (ma.value, mi.value)}
+
+    def launch_count(self) -> int:
+        return int(self._lib.emo_launch_count(self._h))
+
+    def timer_start(self):
+        check(self._lib.emo_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(self._lib.emo_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def mark(self, slot: int):
+        check(self._lib.emo_mark(self._h, slot))
+
+    def mark_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        check(self._lib.emo_mark_elapsed(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self._lib.emo_dev_alloc(self._h, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def dev_free(self, p: int):
+        check(self._lib.emo_dev_free(self._h, C.c_void_p(p)))
+
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """Pinned host buffer as a uint8 numpy array (freed with host_free)."""
+        p = C.c_void_p()
+        check(self._lib.emo_host_alloc(self._h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        arr.flags.writeable = True
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        check(self._lib.emo_host_free(self._h, C.c_void_p(arr.ctypes.data)))
+
+    def h2d(self, dst: int, src: np.ndarray):
+        check(self._lib.emo_copy_h2d(self._h, C.c_void_p(dst), _ptr(src), src.nbytes))
+
+    def d2h(self, dst: np.ndarray, src: int):
+        check(self._lib.emo_copy_d2h(self._h, _ptr(dst), C.c_void_p(src), dst.nbytes))
+
+    def probe_int_pipe(self, which: int) -> float:
+        v = C.c_double()
+        check(self._lib.emo_probe_int_pipe(self._h, which, C.byref(v)))
+        return float(v.value)
+
+    # -- (1) analysis ---------------------------------------------------------------------
+    def analyse_tiles(self, tiles, dim: int) -> np.ndarray:
+        """tiles [T,ts,ts,3] -> [T,dim*dim,3]  (analysis.rs:5-20 over the library, main.rs:786-794)."""
+        tiles = _u8(tiles)
+        if tiles.ndim != 4 or tiles.shape[1] != tiles.shape[2] or tiles.shape[3] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"tiles must be [T,ts,ts,3], got {tiles.shape}")
+        T, ts = tiles.shape[0], tiles.shape[1]
+        out = np.zeros((T, dim * dim, 3), np.uint8)
+        check(self._lib.emo_analyse(self._h, _ptr(tiles), T, ts, dim, _ptr(out)))
+        return out
+
+    def analyse_tiles_fused(self, tiles):
+        """One pass -> (1to1 [T,1,3], 4to1 [T,4,3])."""
+        tiles = _u8(tiles)
+        T, ts = tiles.shape[0], tiles.shape[1]
+        o1 = np.zeros((T, 1, 3), np.uint8)
+        o4 = np.zeros((T, 4, 3), np.uint8)
+        check(self._lib.emo_analyse_fused(self._h, _ptr(tiles), T, ts, _ptr(o1), _ptr(o4)))
+        return o1, o4
+
+    def analyse_dev(self, tiles_dev: int, T: int, ts: int, dim: int, out_dev: int):
+        check(self._lib.emo_analyse_dev(self._h, C.c_void_p(tiles_dev), T, ts, dim, C.c_void_p(out_dev)))
+
+    def analyse_fused_dev(self, tiles_dev: int, T: int, ts: int, out1_dev: int, out4_dev: int):
+        check(self._lib.emo_analyse_fused_dev(self._h, C.c_void_p(tiles_dev), T, ts, C.c_void_p(out1_dev),
+                                              C.c_void_p(out4_dev)))
+
+    # -- (2) library ----------------------------------------------------------------------
+    def set_library(self, colors, tile_px=None):
+        """colors [T,N,3], tile_px [T,ts,ts,3] or None  (tileset.rs:178-190 build_kiddo)."""
+        colors = _u8(colors)
+        if colors.ndim != 3 or colors.shape[2] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"colors must be [T,N,3], got {colors.shape}")
+        T, N = colors.shape[0], colors.shape[1]
+        ts = 0
+        if tile_px is not None:
+            tile_px = _u8(tile_px)
+            if tile_px.ndim != 4 or tile_px.shape[0] != T or tile_px.shape[1] != tile_px.shape[2] or tile_px.shape[3] != 3:
+                raise EmosaicError(EMO_ERR_ARG, f"tile_px must be [T,ts,ts,3] with T={T}, got {tile_px.shape}")
+            ts = tile_px.shape[1]
+        check(self._lib.emo_set_library(self._h, _ptr(colors), _ptr(tile_px), T, N, ts))
+        self.T, self.N, self.dim, self.ts = T, N, _isqrt_exact(N), ts
+
+    def set_library_dev(self, colors_dev: int, tile_px_dev: int, T: int, N: int, ts: int):
+        check(self._lib.emo_set_library_dev(self._h, C.c_void_p(colors_dev), C.c_void_p(tile_px_dev or 0), T, N, ts))
+        self.T, self.N, self.dim, self.ts = T, N, _isqrt_exact(N), ts
+
+    # -- (3) match ------------------------------------------------------------------------
+    def match(self, src):
+        """src [H,W,3] -> (item [H/dim,W/dim] int32 signed 1-based, dist uint32)  (rendering.rs:158-221)."""
+        src = _u8(src)
+        if src.ndim != 3 or src.shape[2] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"src must be [H,W,3], got {src.shape}")
+        H, W = src.shape[:2]
+        d = max(self.dim, 1)
+        item = np.zeros((H // d, W // d), np.int32)
+        dist = np.zeros((H // d, W // d), np.uint32)
+        check(self._lib.emo_match(self._h, _ptr(src), W, H, _ptr(item), _ptr(dist)))
+        return item, dist
+
+    def match_dev(self, src_dev: int, W: int, H: int, item_dev: int, dist_dev: int):
+        check(self._lib.emo_match_dev(self._h, C.c_void_p(src_dev), W, H, C.c_void_p(item_dev), C.c_void_p(dist_dev)))
+
+    # -- (4) compose (+tint) ---------------------------------------------------------------
+    def compose(self, item, src=None, out_channels: int = 3, tint_alpha: int = 0, out: np.ndarray | None = None):
+        """item [bh,bw] (+ src [bh*dim,bw*dim,3] when tinting) -> [bh*ts,bw*ts,out_channels]."""
+        item = np.ascontiguousarray(item, dtype=np.int32)
+        bh, bw = item.shape
+        W, H = bw * self.dim, bh * self.dim
+        if src is not None:
+            src = _u8(src)
+            if src.shape != (H, W, 3):
+                raise EmosaicError(EMO_ERR_ARG, f"src must be {(H, W, 3)}, got {src.shape}")
+        if out is None:
+            out = np.zeros((bh * self.ts, bw * self.ts, out_channels), np.uint8)
+        check(self._lib.emo_compose(self._h, _ptr(item), _ptr(src), W, H, out_channels, tint_alpha, _ptr(out)))
+        return out
+
+    def compose_dev(self, item_dev: int, src_dev: int, W: int, H: int, out_channels: int, tint_alpha: int, out_dev: int):
+        check(self._lib.emo_compose_dev(self._h, C.c_void_p(item_dev), C.c_void_p(src_dev or 0), W, H, out_channels,
+                                        tint_alpha, C.c_void_p(out_dev)))
+
+    def mosaic(self, src, out_channels: int = 3, tint_alpha: int = 0, out: np.ndarray | None = None, want_maps=True):
+        """Whole path with host buffers: match + compose (+tint)."""
+        src = _u8(src)
+        H, W = src.shape[:2]
+        d = max(self.dim, 1)
+        bh, bw = H // d, W // d
+        if out is None:
+            out = np.zeros((bh * self.ts, bw * self.ts, out_channels), np.uint8)
+        item = np.zeros((bh, bw), np.int32) if want_maps else None
+        dist = np.zeros((bh, bw), np.uint32) if want_maps else None
+        check(self._lib.emo_mosaic(self._h, _ptr(src), W, H, out_channels, tint_alpha, _ptr(item), _ptr(dist), _ptr(out)))
+        return out, item, dist
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-shaped interface
+# ---------------------------------------------------------------------------------------------
+def analyse(img, N: int, ctx: Context | None = None) -> np.ndarray:
+    """``analyse::<N>(img)`` (analysis.rs:5-20): square RGB image -> [N,3] cell means."""
+    img = _u8(img)
+    if img.ndim != 3 or img.shape[2] != 3 or img.shape[0] != img.shape[1]:
+        raise EmosaicError(EMO_ERR_ARG, f"analyse: tiles are square RGB images on this path, got {img.shape}")
+    dim = _isqrt_exact(N)
+    return (ctx or default_context()).analyse_tiles(img[None], dim)[0]
+
+
+def analyse_tiles(tiles, N: int, ctx: Context | None = None) -> np.ndarray:
+    return (ctx or default_context()).analyse_tiles(tiles, _isqrt_exact(N))
+
+
+def get_img_colors(x: int, y: int, step: int, source_img, N: int) -> np.ndarray:
+    """``get_img_colors::<N>`` (analysis.rs:23-36).  Host-side view; the match kernel does this gather itself."""
+    source_img = _u8(source_img)
+    out = np.zeros((N, 3), np.uint8)
+    for i in range(N):
+        out[i] = source_img[y + i // step, x + i % step]
+    return out
+
+
+def flipped_coords(coords: Sequence[int]) -> np.ndarray:
+    """tiles/utils.rs:18-43: mirror a flattened [rows*cols*3] coordinate vector row by row."""
+    c = np.array(coords).copy()
+    n = c.size
+    rows = math.isqrt(n // 3)
+    cols = rows
+    cir = cols * 3
+    for i in range(rows):
+        for j in range(cols // 2):
+            a, b = i * cir + j * 3, (i + 1) * cir - (j + 1) * 3
+            for h in range(3):
+                c[a + h], c[b + h] = c[b + h], c[a + h]
+    return c
+
+
+@dataclass
+class Tile:
+    """tiles/tile.rs:9-17."""
+    colors: np.ndarray  # [N,3] u8
+    idx: int = 0
+    flipped: bool = False
+    date_taken: Optional[str] = None
+
+    @staticmethod
+    def from_colors(colors) -> "Tile":
+        return Tile(_u8(colors).reshape(-1, 3), 0)
+
+    def coords(self) -> np.ndarray:
+        """tile.rs:106-119: [3N] u32, r,g,b interleaved, mirrored when flipped."""
+        c = self.colors.reshape(-1).astype(np.uint32)
+        return flipped_coords(c).astype(np.uint32) if self.flipped else c
+
+
+@dataclass
+class TileSet:
+    """tiles/tileset.rs:21-26 — colours, paths and (optionally) in-memory tile images."""
+    N: int
+    colors: List[np.ndarray] = field(default_factory=list)
+    paths: List[str] = field(default_factory=list)
+    dates: List[Optional[str]] = field(default_factory=list)
+    images: dict = field(default_factory=dict)
+
+    def __len__(self):
+        return len(self.colors)
+
+    def push_tile(self, path: str, colors, date_taken: Optional[str] = None):
+        self.colors.append(_u8(colors).reshape(self.N, 3))
+        self.paths.append(path)
+        self.dates.append(date_taken)
+
+    def push_tile_with_image(self, path: str, colors, image):
+        self.push_tile(path, colors)
+        self.images[len(self.colors)] = _u8(image)
+
+    @staticmethod
+    def from_arrays(colors, tile_px=None, paths=None, dates=None) -> "TileSet":
+        colors = _u8(colors)
+        ts = TileSet(N=colors.shape[1])
+        ts.colors = [c for c in colors]
+        ts.paths = list(paths) if paths is not None else [f"tile{i:07d}.jpg" for i in range(len(colors))]
+        ts.dates = list(dates) if dates is not None else [None] * len(colors)
+        if tile_px is not None:
+            ts._px = _u8(tile_px)
+        return ts
+
+    def colors_array(self) -> np.ndarray:
+        return np.ascontiguousarray(np.stack(self.colors), dtype=np.uint8) if self.colors else np.zeros((0, self.N, 3), np.uint8)
+
+    def pixels_array(self, tile_size: int) -> np.ndarray:
+        if getattr(self, "_px", None) is not None:
+            return self._px
+        T = len(self)
+        if len(self.images) != T:
+            raise EmosaicError(EMO_ERR_ARG, "Image not found: tiles without in-memory images must be prepared on the host "
+                               "(prepare_tile is outside the accelerated path)")
+        px = np.stack([self.images[i + 1] for i in range(T)])
+        if px.shape[1] != tile_size or px.shape[2] != tile_size:
+            raise EmosaicError(EMO_ERR_ARG, f"tile images are {px.shape[1:3]}, expected {tile_size}x{tile_size}")
+        return np.ascontiguousarray(px, dtype=np.uint8)
+
+    def get_tile(self, idx: int) -> Optional[Tile]:
+        """tileset.rs:131-143: positive = normal, negative = flipped, 1-based."""
+        a = abs(idx)
+        if a == 0 or a > len(self):
+            return None
+        return Tile(self.colors[a - 1], a, idx < 0, self.dates[a - 1])
+
+    def get_path(self, tile: Tile) -> str:
+        return self.paths[tile.idx - 1]
+
+    def build_kiddo(self, ctx: Context | None = None, tile_size: int | None = None) -> Context:
+        """tileset.rs:178-190: make the (tile, mirrored tile) search set resident on the GPU."""
+        ctx = ctx or default_context()
+        px = self.pixels_array(tile_size) if tile_size else None
+        if len(self) == 0:
+            raise EmosaicError(EMO_ERR_ARG, "empty tile set")
+        ctx.set_library(self.colors_array(), px)
+        return ctx
+
+
+@dataclass
+class RenderResult:
+    """rendering.rs:236-243.  `stats` is the pair of maps the reference's RenderStats is fed with."""
+    image: np.ndarray
+    tile_set: TileSet
+    item: np.ndarray
+    dist: np.ndarray
+
+
+def adjust_source_dims(w: int, h: int, downsample: int, dim: int):
+    """main.rs:567-587: size the source is resized to before matching."""
+    nw, nh = w // downsample, h // downsample
+    m = nw % dim
+    nw = nw + dim - m if m > dim // 2 else nw - m
+    m = nh % dim
+    nh = nh + dim - m if m > dim // 2 else nh - m
+    return nw, nh
+
+
+def tint_alpha(tint_opacity: float) -> int:
+    """main.rs:449 ``(255.0 * tint_opacity) as u8`` (saturating, truncating)."""
+    v = 255.0 * float(tint_opacity)
+    if not (v > 0.0):
+        return 0
+    return 255 if v >= 255.0 else int(v)
+
+
+def render_nto1(source_img, tile_set: TileSet, tile_size: int, no_repeat: bool = False, randomize: Optional[float] = None,
+                tint_opacity: float = 0.0, ctx: Context | None = None) -> RenderResult:
+    """``render_nto1::<N>`` (rendering.rs:124-230) [+ tint block main.rs:447-478 when tint_opacity > 0]."""
+    if no_repeat or randomize is not None:
+        raise EmosaicError(EMO_ERR_UNSUPPORTED, "no_repeat / randomize are order-dependent host algorithms outside the "
+                           "accelerated path (rendering.rs:163-209, :262-401)")
+    source_img = _u8(source_img)
+    dim = _isqrt_exact(tile_set.N)
+    H, W = source_img.shape[:2]
+    if W % dim or H % dim:
+        raise EmosaicError(EMO_ERR_ARG, f"Invalid source dimensions ({W}x{H}): Dimensions must be divisible by {dim}")
+    if tile_size % dim:
+        raise EmosaicError(EMO_ERR_ARG, f"Invalid tile size: Tile size must be divisible by {dim}")
+    ctx = tile_set.build_kiddo(ctx, tile_size)
+    if tint_opacity > 0.0:
+        image, item, dist = ctx.mosaic(source_img, 4, tint_alpha(tint_opacity))
+    else:
+        image, item, dist = ctx.mosaic(source_img, 3, 0)
+    return RenderResult(image, tile_set, item, dist)
+
+
+def apply_tint(output, source_img, tint_opacity: float, tile_set: TileSet, tile_size: int, item,
+               ctx: Context | None = None) -> np.ndarray:
+    """The tint block alone (main.rs:447-478) for an already matched item map: RGBA result."""
+    ctx = tile_set.build_kiddo(ctx, tile_size)
+    return ctx.compose(item, source_img, 4, tint_alpha(tint_opacity))

@@ -1,0 +1,159 @@
+// common.cuh — context, error plumbing and sm_100a PTX helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/emosaic_cuda.h"
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (nothing unwinds across the C ABI)
+// ---------------------------------------------------------------------------------------
+void emo_set_error(const char *fmt, ...);
+
+#define EMO_CK(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            emo_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return e__ == cudaErrorMemoryAllocation ? EMO_ERR_OOM : EMO_ERR_CUDA;                 \
+        }                                                                                         \
+    } while (0)
+
+#define EMO_REQUIRE(cond, code, ...)                                                              \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            emo_set_error(__VA_ARGS__);                                                           \
+            return (code);                                                                        \
+        }                                                                                         \
+    } while (0)
+
+#define EMO_LAUNCH_CHECK(ctx)                                                                     \
+    do {                                                                                          \
+        (ctx)->launches++;                                                                        \
+        EMO_CK(cudaGetLastError());                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct emo_tint_tables {
+    int alpha = -1;           // alpha the tables were built for (-1: none)
+    int K = 0;                // max exceptional bg values per fg (see compose.cu)
+    uint8_t alpha_out = 255;  // trunc(255 * alpha_final)
+    uint8_t *lut = nullptr;   // [256 bg][256 fg] exact f32 blend results          (device)
+    uint8_t *excv = nullptr;  // [4][256 fg] exceptional bg values                   (device)
+    uint8_t *excm = nullptr;  // [4][256 fg] 0x80 where excv is valid                (device)
+    uint32_t *meta = nullptr; // [0] = max exceptions per fg, [1] = alpha byte, [2] = sanity errors (device)
+};
+
+struct emo_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream all work is issued on (own or external)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_pipe[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t launches = 0;
+    std::vector<cudaEvent_t> marks;
+
+    // resident library
+    uint32_t T = 0, N = 0, dim = 0, ts = 0;
+    uint32_t words = 0;       // packed u32 words per candidate vector = ceil(3N/4)
+    uint32_t L = 0;           // real candidates (T for N==1, 2T otherwise)
+    uint32_t chunk = 0;       // candidates per shared-memory stage
+    uint32_t n_chunks = 0;    // Lpad / chunk
+    uint32_t *cand = nullptr; // [n_chunks*chunk][words]
+    size_t cand_cap = 0;
+    uint8_t *lib_px = nullptr; // [2T][ts][ts][3]: entry 2t = tile t, 2t+1 = tile t mirrored
+    size_t lib_cap = 0;
+    bool has_px = false;
+
+    // scratch
+    unsigned long long *keys = nullptr;  // [Q] packed (dist<<32 | candidate) for split matching
+    size_t keys_cap = 0;
+    int *err_flag = nullptr;             // device: bit0 = item out of range in compose
+    void *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // device staging for the host API
+    size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
+
+    emo_tint_tables tint;
+};
+
+int emo_ensure(emo_ctx *ctx, void **p, size_t *cap, size_t bytes);  // grow-only device buffer
+int emo_check_device_flag(emo_ctx *ctx);
+
+// kernels' host launchers (device pointers, async on ctx->stream)
+int emo_launch_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out);
+int emo_launch_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4);
+int emo_launch_build_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px);
+int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);
+int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t W, uint32_t H,
+                       uint32_t out_channels, uint8_t tint_alpha, uint8_t *out);
+int emo_prepare_tint(emo_ctx *ctx, uint8_t alpha);
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;  // SASS: VABSDIFF4.U8.ACC — c + sum over the 4 bytes of |a_i - b_i|
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_cs_v4(void *p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_cs_v2(void *p, uint2 v) {
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_cs_u32(void *p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif

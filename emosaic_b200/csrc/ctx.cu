@@ -1,0 +1,476 @@
+// ctx.cu — context management and the host-pointer halves of the C ABI (include/emosaic_cuda.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+void emo_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+extern "C" {
+
+int emo_abi_version(void) { return EMO_ABI_VERSION; }
+const char *emo_last_error(void) { return g_last_error.c_str(); }
+
+int emo_create(int device, emo_ctx **out) {
+    EMO_REQUIRE(out != nullptr, EMO_ERR_ARG, "emo_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        emo_set_error("emo_create: no CUDA device (%s); this library has no CPU path",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return EMO_ERR_NO_DEVICE;
+    }
+    EMO_REQUIRE(device >= 0 && device < n, EMO_ERR_ARG, "emo_create: device %d out of range [0,%d)", device, n);
+    EMO_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EMO_CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        emo_set_error("emo_create: device %d (%s, cc %d.%d) is not sm_100; kernels are built for sm_100a only",
+                      device, prop.name, prop.major, prop.minor);
+        return EMO_ERR_NO_DEVICE;
+    }
+    emo_ctx *ctx = new emo_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    EMO_CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    EMO_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    EMO_CK(cudaEventCreate(&ctx->ev_start));
+    EMO_CK(cudaEventCreate(&ctx->ev_stop));
+    for (int i = 0; i < 4; i++) EMO_CK(cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
+    EMO_CK(cudaMalloc(&ctx->err_flag, sizeof(int)));
+    EMO_CK(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+    *out = ctx;
+    return EMO_OK;
+}
+
+void emo_destroy(emo_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->cand);
+    cudaFree(ctx->lib_px);
+    cudaFree(ctx->keys);
+    cudaFree(ctx->err_flag);
+    for (int i = 0; i < 6; i++) cudaFree(ctx->stage[i]);
+    cudaFree(ctx->tint.lut);
+    cudaFree(ctx->tint.excv);
+    cudaFree(ctx->tint.excm);
+    cudaFree(ctx->tint.meta);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
+    for (cudaEvent_t e : ctx->marks)
+        if (e) cudaEventDestroy(e);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int emo_set_stream(emo_ctx *ctx, void *cuda_stream) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_stream: ctx is NULL");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return EMO_OK;
+}
+
+int emo_sync(emo_ctx *ctx) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_sync: ctx is NULL");
+    EMO_CK(cudaSetDevice(ctx->device));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->copy_stream));
+    return emo_check_device_flag(ctx);
+}
+
+int emo_device_info(emo_ctx *ctx, char *name, size_t name_cap, int *sm_count, int *cc_major, int *cc_minor) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_device_info: ctx is NULL");
+    cudaDeviceProp prop;
+    EMO_CK(cudaGetDeviceProperties(&prop, ctx->device));
+    if (name && name_cap) {
+        strncpy(name, prop.name, name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return EMO_OK;
+}
+
+uint64_t emo_launch_count(emo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int emo_timer_start(emo_ctx *ctx) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_timer_start: ctx is NULL");
+    EMO_CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    return EMO_OK;
+}
+
+int emo_timer_stop(emo_ctx *ctx, float *elapsed_ms) {
+    EMO_REQUIRE(ctx && elapsed_ms, EMO_ERR_ARG, "emo_timer_stop: NULL argument");
+    EMO_CK(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    EMO_CK(cudaEventSynchronize(ctx->ev_stop));
+    EMO_CK(cudaEventElapsedTime(elapsed_ms, ctx->ev_start, ctx->ev_stop));
+    return EMO_OK;
+}
+
+int emo_mark(emo_ctx *ctx, uint32_t slot) {
+    EMO_REQUIRE(ctx && slot < 65536, EMO_ERR_ARG, "emo_mark: bad argument");
+    if (ctx->marks.size() <= slot) ctx->marks.resize(slot + 1, nullptr);
+    if (!ctx->marks[slot]) EMO_CK(cudaEventCreate(&ctx->marks[slot]));
+    EMO_CK(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return EMO_OK;
+}
+
+int emo_mark_elapsed(emo_ctx *ctx, uint32_t a, uint32_t b, float *elapsed_ms) {
+    EMO_REQUIRE(ctx && elapsed_ms && a < ctx->marks.size() && b < ctx->marks.size() && ctx->marks[a] && ctx->marks[b],
+                EMO_ERR_ARG, "emo_mark_elapsed: unknown mark");
+    EMO_CK(cudaEventSynchronize(ctx->marks[b]));
+    EMO_CK(cudaEventElapsedTime(elapsed_ms, ctx->marks[a], ctx->marks[b]));
+    return EMO_OK;
+}
+
+int emo_dev_alloc(emo_ctx *ctx, size_t bytes, void **out) {
+    EMO_REQUIRE(ctx && out, EMO_ERR_ARG, "emo_dev_alloc: NULL argument");
+    EMO_CK(cudaSetDevice(ctx->device));
+    EMO_CK(cudaMalloc(out, bytes ? bytes : 1));
+    return EMO_OK;
+}
+int emo_dev_free(emo_ctx *ctx, void *p) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_dev_free: ctx is NULL");
+    EMO_CK(cudaFree(p));
+    return EMO_OK;
+}
+int emo_host_alloc(emo_ctx *ctx, size_t bytes, void **out) {
+    EMO_REQUIRE(ctx && out, EMO_ERR_ARG, "emo_host_alloc: NULL argument");
+    EMO_CK(cudaSetDevice(ctx->device));
+    EMO_CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return EMO_OK;
+}
+int emo_host_free(emo_ctx *ctx, void *p) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_host_free: ctx is NULL");
+    EMO_CK(cudaFreeHost(p));
+    return EMO_OK;
+}
+int emo_copy_h2d(emo_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    EMO_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), EMO_ERR_ARG, "emo_copy_h2d: NULL argument");
+    EMO_CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return EMO_OK;
+}
+int emo_copy_d2h(emo_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    EMO_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), EMO_ERR_ARG, "emo_copy_d2h: NULL argument");
+    EMO_CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return EMO_OK;
+}
+
+}  // extern "C"
+
+int emo_ensure(emo_ctx *ctx, void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *p) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    if (*p) {
+        EMO_CK(cudaStreamSynchronize(ctx->stream));
+        EMO_CK(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        emo_set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        *p = nullptr;
+        return EMO_ERR_OOM;
+    }
+    *cap = want;
+    return EMO_OK;
+}
+
+int emo_check_device_flag(emo_ctx *ctx) {
+    int flag = 0;
+    EMO_CK(cudaMemcpy(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        EMO_CK(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+        emo_set_error("compose: item map holds 0 or an id beyond the library (reference: tileset.rs:131-143 get_tile -> None, "
+                      "rendering.rs:198-206 panics)");
+        return EMO_ERR_ARG;
+    }
+    return EMO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI: device-pointer variants (thin argument checks + launchers) and host-pointer variants
+// ---------------------------------------------------------------------------------------
+static int check_analyse_args(const void *tiles, uint64_t T, uint32_t ts, uint32_t dim, const void *out) {
+    EMO_REQUIRE(T == 0 || (tiles && out), EMO_ERR_ARG, "analyse: NULL buffer");
+    EMO_REQUIRE(ts >= 1 && ts <= 4096, EMO_ERR_ARG, "analyse: tile size %u outside [1,4096]", ts);
+    // color.rs:18 "Rectangle dimensions must be positive": floor(ts/dim) == 0 panics in the reference
+    EMO_REQUIRE(dim >= 1 && dim <= ts, EMO_ERR_ARG,
+                "analyse: dim %u gives an empty cell for tile size %u (Rectangle dimensions must be positive)", dim, ts);
+    return EMO_OK;
+}
+
+extern "C" {
+
+int emo_analyse_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse_dev: ctx is NULL");
+    int rc = check_analyse_args(tiles, T, ts, dim, out);
+    if (rc) return rc;
+    if (T == 0) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_analyse(ctx, tiles, T, ts, dim, out);
+}
+
+int emo_analyse_fused_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse_fused_dev: ctx is NULL");
+    int rc = check_analyse_args(tiles, T, ts, 2, out1);
+    if (rc) return rc;
+    EMO_REQUIRE(T == 0 || out4, EMO_ERR_ARG, "analyse_fused: out4 is NULL");
+    EMO_REQUIRE(ts % 2 == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by 2");  // main.rs:612-615
+    if (T == 0) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_analyse_fused(ctx, tiles, T, ts, out1, out4);
+}
+
+int emo_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse: ctx is NULL");
+    int rc = check_analyse_args(tiles, T, ts, dim, out);
+    if (rc) return rc;
+    if (T == 0) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    size_t in_b = (size_t)T * ts * ts * 3, out_b = (size_t)T * dim * dim * 3;
+    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], in_b))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], out_b))) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[0], tiles, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = emo_launch_analyse(ctx, (const uint8_t *)ctx->stage[0], T, ts, dim, (uint8_t *)ctx->stage[1]))) return rc;
+    EMO_CK(cudaMemcpyAsync(out, ctx->stage[1], out_b, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
+int emo_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse_fused: ctx is NULL");
+    int rc = check_analyse_args(tiles, T, ts, 2, out1);
+    if (rc) return rc;
+    EMO_REQUIRE(T == 0 || out4, EMO_ERR_ARG, "analyse_fused: out4 is NULL");
+    EMO_REQUIRE(ts % 2 == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by 2");
+    if (T == 0) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    size_t in_b = (size_t)T * ts * ts * 3;
+    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], in_b))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], (size_t)T * 15))) return rc;
+    uint8_t *d1 = (uint8_t *)ctx->stage[1], *d4 = d1 + (size_t)T * 3;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[0], tiles, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = emo_launch_analyse_fused(ctx, (const uint8_t *)ctx->stage[0], T, ts, d1, d4))) return rc;
+    EMO_CK(cudaMemcpyAsync(out1, d1, (size_t)T * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaMemcpyAsync(out4, d4, (size_t)T * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
+static int check_library_args(const void *colors, uint32_t T, uint32_t N, uint32_t ts, const void *px) {
+    EMO_REQUIRE(colors, EMO_ERR_ARG, "set_library: colors is NULL");
+    EMO_REQUIRE(T >= 1 && T < (1u << 30), EMO_ERR_ARG, "set_library: T=%u outside [1,2^30)", T);
+    uint32_t dim = 1;
+    while (dim * dim < N) dim++;
+    EMO_REQUIRE(N >= 1 && dim * dim == N, EMO_ERR_ARG, "set_library: N=%u is not a square", N);
+    if (px) {
+        EMO_REQUIRE(ts >= 1 && ts <= 4096, EMO_ERR_ARG, "set_library: tile size %u outside [1,4096]", ts);
+        EMO_REQUIRE(ts % dim == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by %u", dim);  // main.rs:612-615
+    }
+    return EMO_OK;
+}
+
+static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, bool has_px) {
+    uint32_t dim = 1;
+    while (dim * dim < N) dim++;
+    uint32_t words = (3 * N + 3) / 4;
+    if (!(words == 1 || words == 3 || words == 7 || words == 12)) {
+        emo_set_error("set_library: N=%u (--mode %u) is not built into this library yet; supported N: 1, 4, 9, 16", N, dim);
+        return EMO_ERR_UNSUPPORTED;
+    }
+    ctx->T = T; ctx->N = N; ctx->dim = dim; ctx->ts = ts; ctx->words = words;
+    ctx->L = (N == 1) ? T : 2 * T;  // for N == 1 a tile and its mirror coincide; the mirror can never win a tie
+    uint32_t chunk = (words == 1) ? 2048 : (words == 3 ? 1024 : 256);
+    uint32_t l16 = (ctx->L + 15) / 16 * 16;
+    if (l16 < chunk) chunk = l16;
+    ctx->chunk = chunk;
+    ctx->n_chunks = (ctx->L + chunk - 1) / chunk;
+    ctx->has_px = has_px;
+    int rc;
+    if ((rc = emo_ensure(ctx, (void **)&ctx->cand, &ctx->cand_cap, (size_t)ctx->n_chunks * chunk * words * 4))) return rc;
+    if (has_px && (rc = emo_ensure(ctx, (void **)&ctx->lib_px, &ctx->lib_cap, (size_t)2 * T * ts * ts * 3))) return rc;
+    return EMO_OK;
+}
+
+int emo_set_library_dev(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_library_dev: ctx is NULL");
+    int rc = check_library_args(colors, T, N, ts, tile_px);
+    if (rc) return rc;
+    EMO_CK(cudaSetDevice(ctx->device));
+    ctx->T = 0;
+    if ((rc = library_common(ctx, T, N, ts, tile_px != nullptr))) { ctx->T = 0; return rc; }
+    return emo_launch_build_library(ctx, colors, tile_px);
+}
+
+int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_library: ctx is NULL");
+    int rc = check_library_args(colors, T, N, ts, tile_px);
+    if (rc) return rc;
+    EMO_CK(cudaSetDevice(ctx->device));
+    ctx->T = 0;
+    if ((rc = library_common(ctx, T, N, ts, tile_px != nullptr))) { ctx->T = 0; return rc; }
+    size_t cb = (size_t)T * N * 3, pb = tile_px ? (size_t)T * ts * ts * 3 : 0;
+    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], cb))) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[0], colors, cb, cudaMemcpyHostToDevice, ctx->stream));
+    if (tile_px) {
+        if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], pb))) return rc;
+        EMO_CK(cudaMemcpyAsync(ctx->stage[1], tile_px, pb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = emo_launch_build_library(ctx, (const uint8_t *)ctx->stage[0], tile_px ? (const uint8_t *)ctx->stage[1] : nullptr)))
+        return rc;
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
+static int check_match_args(emo_ctx *ctx, const void *src, uint32_t W, uint32_t H) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "match: ctx is NULL");
+    EMO_REQUIRE(ctx->T > 0, EMO_ERR_STATE, "match: no library set (call emo_set_library first)");
+    EMO_REQUIRE(src, EMO_ERR_ARG, "match: src is NULL");
+    EMO_REQUIRE(W > 0 && H > 0, EMO_ERR_ARG, "match: empty source %ux%u", W, H);
+    // main.rs:603-611
+    EMO_REQUIRE(W % ctx->dim == 0 && H % ctx->dim == 0, EMO_ERR_ARG,
+                "Invalid source dimensions (%ux%u): Dimensions must be divisible by %u", W, H, ctx->dim);
+    EMO_REQUIRE((uint64_t)(W / ctx->dim) * (H / ctx->dim) < (1ull << 31), EMO_ERR_ARG, "match: too many blocks");
+    return EMO_OK;
+}
+
+int emo_match_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    int rc = check_match_args(ctx, src, W, H);
+    if (rc) return rc;
+    EMO_REQUIRE(item && dist, EMO_ERR_ARG, "match: item/dist is NULL");
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_match(ctx, src, W, H, item, dist);
+}
+
+int emo_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    int rc = check_match_args(ctx, src, W, H);
+    if (rc) return rc;
+    EMO_REQUIRE(item && dist, EMO_ERR_ARG, "match: item/dist is NULL");
+    EMO_CK(cudaSetDevice(ctx->device));
+    size_t sb = (size_t)W * H * 3, Q = (size_t)(W / ctx->dim) * (H / ctx->dim);
+    if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], sb))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], Q * 4))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[4], &ctx->stage_cap[4], Q * 4))) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[2], src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = emo_launch_match(ctx, (const uint8_t *)ctx->stage[2], W, H, (int32_t *)ctx->stage[3], (uint32_t *)ctx->stage[4])))
+        return rc;
+    EMO_CK(cudaMemcpyAsync(item, ctx->stage[3], Q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaMemcpyAsync(dist, ctx->stage[4], Q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
+static int check_compose_args(emo_ctx *ctx, const void *item, const void *src, uint32_t W, uint32_t H, uint32_t oc,
+                              const void *out) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "compose: ctx is NULL");
+    EMO_REQUIRE(ctx->T > 0 && ctx->has_px, EMO_ERR_STATE, "compose: no tile pixels resident (emo_set_library with tile_px)");
+    EMO_REQUIRE(item && out, EMO_ERR_ARG, "compose: item/out is NULL");
+    EMO_REQUIRE(oc == 3 || oc == 4, EMO_ERR_ARG, "compose: out_channels must be 3 (RGB) or 4 (RGBA + tint), got %u", oc);
+    EMO_REQUIRE(oc == 3 || src, EMO_ERR_ARG, "compose: tint needs the source image");
+    EMO_REQUIRE(W > 0 && H > 0 && W % ctx->dim == 0 && H % ctx->dim == 0, EMO_ERR_ARG,
+                "Invalid source dimensions (%ux%u): Dimensions must be divisible by %u", W, H, ctx->dim);
+    return EMO_OK;
+}
+
+int emo_compose_dev(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc,
+                    uint8_t tint_alpha, uint8_t *out) {
+    int rc = check_compose_args(ctx, item, src, W, H, oc, out);
+    if (rc) return rc;
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_compose(ctx, item, src, W, H, oc, tint_alpha, out);
+}
+
+int emo_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc,
+                uint8_t tint_alpha, uint8_t *out) {
+    int rc = check_compose_args(ctx, item, src, W, H, oc, out);
+    if (rc) return rc;
+    EMO_CK(cudaSetDevice(ctx->device));
+    uint32_t bw = W / ctx->dim, bh = H / ctx->dim;
+    size_t Q = (size_t)bw * bh, ob = Q * ctx->ts * ctx->ts * oc, sb = (size_t)W * H * 3;
+    if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], Q * 4))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[5], &ctx->stage_cap[5], ob))) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[3], item, Q * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t *dsrc = nullptr;
+    if (oc == 4) {
+        if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], sb))) return rc;
+        EMO_CK(cudaMemcpyAsync(ctx->stage[2], src, sb, cudaMemcpyHostToDevice, ctx->stream));
+        dsrc = (const uint8_t *)ctx->stage[2];
+    }
+    if ((rc = emo_launch_compose(ctx, (const int32_t *)ctx->stage[3], dsrc, W, H, oc, tint_alpha, (uint8_t *)ctx->stage[5])))
+        return rc;
+    EMO_CK(cudaMemcpyAsync(out, ctx->stage[5], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return emo_check_device_flag(ctx);
+}
+
+// Whole path with host buffers: the source goes up once, then block-row chunks are matched and
+// composed on the compute stream while the previous chunk's output drains to the host on the
+// copy stream (two device output buffers).
+int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha,
+               int32_t *item, uint32_t *dist, uint8_t *out) {
+    int rc = check_match_args(ctx, src, W, H);
+    if (rc) return rc;
+    EMO_REQUIRE(ctx->has_px, EMO_ERR_STATE, "mosaic: no tile pixels resident (emo_set_library with tile_px)");
+    EMO_REQUIRE(out, EMO_ERR_ARG, "mosaic: out is NULL");
+    EMO_REQUIRE(oc == 3 || oc == 4, EMO_ERR_ARG, "mosaic: out_channels must be 3 or 4, got %u", oc);
+    EMO_CK(cudaSetDevice(ctx->device));
+    const uint32_t dim = ctx->dim, ts = ctx->ts, bw = W / dim, bh = H / dim;
+    const size_t Q = (size_t)bw * bh, sb = (size_t)W * H * 3;
+    const size_t row_out = (size_t)bw * ts * ts * oc;  // output bytes per block row
+    // chunk: ~64 MB of output per step, at least one block row
+    uint32_t rows_per_chunk = (uint32_t)((64ull << 20) / (row_out ? row_out : 1));
+    if (rows_per_chunk < 1) rows_per_chunk = 1;
+    if (rows_per_chunk > bh) rows_per_chunk = bh;
+    const size_t chunk_out = row_out * rows_per_chunk;
+    if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], sb))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], Q * 4))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[4], &ctx->stage_cap[4], Q * 4))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[5], &ctx->stage_cap[5], chunk_out * 2))) return rc;
+    uint8_t *dsrc = (uint8_t *)ctx->stage[2];
+    int32_t *ditem = (int32_t *)ctx->stage[3];
+    uint32_t *ddist = (uint32_t *)ctx->stage[4];
+    uint8_t *dout[2] = {(uint8_t *)ctx->stage[5], (uint8_t *)ctx->stage[5] + chunk_out};
+    EMO_CK(cudaMemcpyAsync(dsrc, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t k = 0;
+    for (uint32_t r0 = 0; r0 < bh; r0 += rows_per_chunk, k++) {
+        uint32_t nr = bh - r0 < rows_per_chunk ? bh - r0 : rows_per_chunk;
+        const uint8_t *s = dsrc + (size_t)r0 * dim * W * 3;
+        int b = k & 1;
+        if ((rc = emo_launch_match(ctx, s, W, nr * dim, ditem + (size_t)r0 * bw, ddist + (size_t)r0 * bw))) return rc;
+        // the buffer must have drained (chunk k-2) before it is overwritten
+        if (k >= 2) EMO_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[2 + b], 0));
+        if ((rc = emo_launch_compose(ctx, ditem + (size_t)r0 * bw, s, W, nr * dim, oc, tint_alpha, dout[b]))) return rc;
+        EMO_CK(cudaEventRecord(ctx->ev_pipe[b], ctx->stream));
+        EMO_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[b], 0));
+        EMO_CK(cudaMemcpyAsync(out + (size_t)r0 * row_out, dout[b], (size_t)nr * row_out, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+        EMO_CK(cudaEventRecord(ctx->ev_pipe[2 + b], ctx->copy_stream));
+    }
+    if (item) EMO_CK(cudaMemcpyAsync(item, ditem, Q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist) EMO_CK(cudaMemcpyAsync(dist, ddist, Q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->copy_stream));
+    return emo_check_device_flag(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// match.cu — search-set build and brute-force L1 nearest-colour matching.
+//
+// Reference: TileSet::build_kiddo() src/mosaic/tiles/tileset.rs:178-190 (every tile enters the
+// KD-tree twice: (coords,+idx) then (mirror(coords),-idx)), Tile::coords() tiles/tile.rs:106-119,
+// flipped_coords() tiles/utils.rs:18-43, get_img_colors() analysis.rs:23-36 and the query
+// kdtree.nearest_one::<Manhattan>() in render_nto1's closure, rendering.rs:158-221.
+//
+// Semantics reproduced exactly: dist = sum over the 3N bytes of |q - c| (u32); winner = minimum
+// distance, ties broken by insertion rank (rank 2t = tile t unflipped, 2t+1 = tile t mirrored),
+// i.e. smallest idx first and unflipped before flipped — kiddo's leaf scan replaces the best only
+// on strict `<`.  item = +(t+1) / -(t+1).
+//
+// Why CUDA cores: L1 distance is not bilinear, so there is no exact tensor-core contraction; the
+// only exact embedding (thermometer codes, |a-b| = popc(ta^tb)) needs K = 765*N per pair and an
+// epilogue that still does one min per pair on the CUDA cores, which costs more than this kernel's
+// whole inner loop.  The inner loop is byte-SIMD instead: one VABSDIFF4.U8.ACC per 4 bytes of
+// vector per pair plus half a VIMNMX3 per pair.
+//
+// Data layout in HBM: candidates packed [Lpad][WORDS] u32 (WORDS = ceil(3N/4), bytes of the
+// 3N-vector little-endian, zero padded), padded to a multiple of the stage size with copies of
+// the last real candidate (a duplicate of an earlier candidate can never win under strict `<`).
+// A CTA keeps NT*R queries in registers and streams the whole candidate array through a
+// 4-stage shared-memory ring filled by TMA bulk copies issued from a dedicated producer warp;
+// every candidate word is read with a warp-broadcast LDS.128 and reused for R queries.
+// The running minimum is distance-only; the argmin is recovered lazily: after each window of 16
+// candidates the thread checks whether any of its minima dropped and only then rescans that
+// window for the first candidate that reaches the new minimum (an improvement happens O(log L)
+// times per query, so the rescan is rare and the common path is 1.5 instructions per pair).
+#include "common.cuh"
+
+static constexpr int MATCH_STAGES = 4;
+static constexpr int MATCH_WIN = 16;
+
+// ---------------------------------------------------------------------------------------
+// library build: packed candidates and the (tile, mirrored tile) pixel store
+// ---------------------------------------------------------------------------------------
+__global__ void build_candidates_kernel(const uint8_t *__restrict__ colors, uint32_t T, uint32_t N, uint32_t dim,
+                                        uint32_t words, uint32_t L, uint32_t Lpad, uint32_t *__restrict__ cand) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Lpad) return;
+    const uint32_t cc = c < L ? c : L - 1;
+    const uint32_t t = (N == 1) ? cc : (cc >> 1);
+    const bool flipped = (N != 1) && (cc & 1);
+    const uint8_t *v = colors + (size_t)t * N * 3;
+    for (uint32_t w = 0; w < words; w++) {
+        uint32_t packed = 0;
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t b = w * 4 + k;  // byte index in the 3N vector
+            if (b < 3 * N) {
+                uint32_t cell = b / 3, ch = b % 3;
+                if (flipped) {  // utils.rs:18-43: swap cell column j <-> dim-1-j inside each cell row
+                    const uint32_t row = cell / dim, col = cell % dim;
+                    cell = row * dim + (dim - 1 - col);
+                }
+                packed |= (uint32_t)v[cell * 3 + ch] << (8 * k);
+            }
+        }
+        cand[(size_t)c * words + w] = packed;
+    }
+}
+
+// lib_px[2t] = tile t, lib_px[2t+1] = tile t mirrored horizontally (tileset.rs:156-157 flip_horizontal),
+// so that compose is a pure gather.
+__global__ void build_pixels_kernel(const uint8_t *__restrict__ px, uint32_t T, uint32_t ts, uint8_t *__restrict__ lib) {
+    const uint64_t total = (uint64_t)T * ts * ts;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = i / ((uint64_t)ts * ts);
+        const uint32_t rem = (uint32_t)(i % ((uint64_t)ts * ts));
+        const uint32_t r = rem / ts, c = rem % ts;
+        const uint8_t *s = px + i * 3;
+        const uint8_t a = s[0], b = s[1], d = s[2];
+        uint8_t *o0 = lib + ((size_t)(2 * t) * ts * ts + (size_t)r * ts + c) * 3;
+        uint8_t *o1 = lib + ((size_t)(2 * t + 1) * ts * ts + (size_t)r * ts + (ts - 1 - c)) * 3;
+        o0[0] = a; o0[1] = b; o0[2] = d;
+        o1[0] = a; o1[1] = b; o1[2] = d;
+    }
+}
+
+int emo_launch_build_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px) {
+    const uint32_t Lpad = ctx->n_chunks * ctx->chunk;
+    build_candidates_kernel<<<(Lpad + 255) / 256, 256, 0, ctx->stream>>>(colors, ctx->T, ctx->N, ctx->dim, ctx->words, ctx->L,
+                                                                        Lpad, ctx->cand);
+    EMO_LAUNCH_CHECK(ctx);
+    if (tile_px) {
+        uint64_t total = (uint64_t)ctx->T * ctx->ts * ctx->ts;
+        uint64_t blocks = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+        build_pixels_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(tile_px, ctx->T, ctx->ts, ctx->lib_px);
+        EMO_LAUNCH_CHECK(ctx);
+    }
+    return EMO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// match kernel
+// ---------------------------------------------------------------------------------------
+struct MatchParams {
+    const uint32_t *cand;   // [n_chunks*chunk][WORDS]
+    uint32_t chunk;         // candidates per stage (multiple of MATCH_WIN)
+    uint32_t n_chunks;      // total stages in the candidate array
+    uint32_t chunks_per_split;
+    const uint8_t *src;     // [H][W][3]
+    uint32_t W, bw, Q, dim;
+    uint32_t mirrored;      // 1: candidate c -> tile c>>1, flipped c&1 ; 0: candidate c -> tile c
+    int32_t *item;
+    uint32_t *dist;
+    unsigned long long *keys;  // non-null: split mode, atomicMin of (dist<<32 | candidate)
+};
+
+template <int WORDS, int OFF, int NCW>
+__device__ __forceinline__ uint32_t sad_vec(const uint32_t (&q)[WORDS], const uint32_t (&c)[NCW]) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) d = sad4(q[w], c[OFF + w], d);
+    return d;
+}
+
+// Same distance for the rare rescan path. `volatile` keeps the compiler from merging the rescan
+// with the main loop (which would put a compare+select on every pair).
+template <int WORDS>
+__device__ __forceinline__ uint32_t sad_vec_rescan(const uint32_t (&q)[WORDS], const uint32_t *c) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) {
+        uint32_t t;
+        asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(t) : "r"(q[w]), "r"(c[w]), "r"(d));
+        d = t;
+    }
+    return d;
+}
+
+template <int WORDS, int R, int NT>
+__global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const MatchParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t stage_words = p.chunk * WORDS;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)MATCH_STAGES * stage_words * 4);
+    uint64_t *empty = full + MATCH_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int CONSUMER_WARPS = NT / 32;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < MATCH_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint32_t c0 = blockIdx.y * p.chunks_per_split;
+    const uint32_t c1 = min(c0 + p.chunks_per_split, p.n_chunks);
+
+    if (warp == CONSUMER_WARPS) {
+        // ---- producer warp: one lane streams candidate stages through the ring with TMA bulk copies
+        if (lane == 0) {
+            const uint32_t bytes = stage_words * 4;
+            for (uint32_t c = c0, n = 0; c < c1; c++, n++) {
+                const int s = n % MATCH_STAGES;
+                if (n >= MATCH_STAGES) mbar_wait(&empty[s], ((n / MATCH_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(ring + (size_t)s * stage_words, p.cand + (size_t)c * stage_words, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: R queries per thread, packed like the candidates
+    uint32_t q[R][WORDS], best[R], seen[R], idx[R];
+    const uint32_t qbase = blockIdx.x * (uint32_t)(NT * R);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint32_t qi = qbase + r * NT + tid;
+        if (qi >= p.Q) qi = p.Q - 1;
+        const uint32_t by = qi / p.bw, bx = qi % p.bw;
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) q[r][w] = 0;
+        // analysis.rs:23-36: cell i of the block is source pixel (x + i % dim, y + i / dim)
+        for (uint32_t i = 0; i < p.dim * p.dim; i++) {
+            const uint8_t *px = p.src + ((size_t)(by * p.dim + i / p.dim) * p.W + (bx * p.dim + i % p.dim)) * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const uint32_t b = i * 3 + ch;
+                const uint32_t v = (uint32_t)px[ch] << (8 * (b & 3));
+#pragma unroll
+                for (int w = 0; w < WORDS; w++)
+                    if ((b >> 2) == (uint32_t)w) q[r][w] |= v;
+            }
+        }
+        best[r] = 0xffffffffu;
+        seen[r] = 0xffffffffu;
+        idx[r] = 0;
+    }
+
+    for (uint32_t c = c0, n = 0; c < c1; c++, n++) {
+        const int s = n % MATCH_STAGES;
+        mbar_wait(&full[s], (n / MATCH_STAGES) & 1);
+        const uint32_t *st = ring + (size_t)s * stage_words;
+        const uint32_t cand_base = c * p.chunk;
+        for (uint32_t w0 = 0; w0 < p.chunk; w0 += MATCH_WIN) {
+            const uint4 *win = reinterpret_cast<const uint4 *>(st + (size_t)w0 * WORDS);
+#pragma unroll 2
+            for (int j4 = 0; j4 < MATCH_WIN / 4; j4++) {
+                // 4 candidates = 4*WORDS words = WORDS x LDS.128 (same address in every lane: broadcast)
+                uint32_t cw[4 * WORDS];
+#pragma unroll
+                for (int v = 0; v < WORDS; v++) {
+                    const uint4 t4 = win[j4 * WORDS + v];
+                    cw[4 * v + 0] = t4.x; cw[4 * v + 1] = t4.y; cw[4 * v + 2] = t4.z; cw[4 * v + 3] = t4.w;
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint32_t d0 = sad_vec<WORDS, 0 * WORDS>(q[r], cw);
+                    const uint32_t d1 = sad_vec<WORDS, 1 * WORDS>(q[r], cw);
+                    const uint32_t d2 = sad_vec<WORDS, 2 * WORDS>(q[r], cw);
+                    const uint32_t d3 = sad_vec<WORDS, 3 * WORDS>(q[r], cw);
+                    best[r] = min(best[r], min(d0, d1));  // VIMNMX3
+                    best[r] = min(best[r], min(d2, d3));
+                }
+            }
+            bool improved = false;
+#pragma unroll
+            for (int r = 0; r < R; r++) improved |= best[r] < seen[r];
+            if (improved) {
+                // rare: find the FIRST candidate of this window that reaches the new minimum
+                const uint32_t *wc = st + (size_t)w0 * WORDS;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (best[r] < seen[r]) {
+                        uint32_t found = 0;
+#pragma unroll
+                        for (int j = MATCH_WIN - 1; j >= 0; j--)
+                            if (sad_vec_rescan<WORDS>(q[r], wc + j * WORDS) == best[r]) found = j;
+                        idx[r] = cand_base + w0 + found;
+                        seen[r] = best[r];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const uint32_t qi = qbase + r * NT + tid;
+        if (qi >= p.Q) continue;
+        if (p.keys) {
+            atomicMin(&p.keys[qi], ((unsigned long long)best[r] << 32) | idx[r]);
+        } else {
+            const uint32_t cnd = idx[r];
+            const int32_t t1 = (int32_t)(p.mirrored ? (cnd >> 1) : cnd) + 1;
+            p.item[qi] = (p.mirrored && (cnd & 1)) ? -t1 : t1;
+            p.dist[qi] = best[r];
+        }
+    }
+}
+
+__global__ void match_init_keys_kernel(unsigned long long *keys, uint32_t Q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Q) keys[i] = ~0ull;
+}
+
+__global__ void match_finalize_kernel(const unsigned long long *__restrict__ keys, uint32_t Q, uint32_t mirrored,
+                                      int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    const unsigned long long k = keys[i];
+    const uint32_t cnd = (uint32_t)k;
+    const int32_t t1 = (int32_t)(mirrored ? (cnd >> 1) : cnd) + 1;
+    item[i] = (mirrored && (cnd & 1)) ? -t1 : t1;
+    dist[i] = (uint32_t)(k >> 32);
+}
+
+template <int WORDS, int R, int NT>
+static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
+    auto kern = match_kernel<WORDS, R, NT>;
+    const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8;
+    EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
+    // split the candidate range across CTAs when the query tiles alone cannot fill the GPU
+    uint32_t splits = 1;
+    const uint32_t want = (uint32_t)ctx->sm_count * 4;
+    if (qtiles < want) {
+        splits = (want + qtiles - 1) / qtiles;
+        if (splits > p.n_chunks) splits = p.n_chunks;
+        if (splits > 65535) splits = 65535;
+    }
+    p.chunks_per_split = (p.n_chunks + splits - 1) / splits;
+    splits = (p.n_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    if (splits > 1) {
+        int rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, (size_t)Q * 8);
+        if (rc) return rc;
+        p.keys = ctx->keys;
+        match_init_keys_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q);
+        EMO_LAUNCH_CHECK(ctx);
+    } else {
+        p.keys = nullptr;
+    }
+    dim3 grid(qtiles, splits);
+    kern<<<grid, NT + 32, smem, ctx->stream>>>(p);
+    EMO_LAUNCH_CHECK(ctx);
+    if (splits > 1) {
+        match_finalize_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, p.mirrored, p.item, p.dist);
+        EMO_LAUNCH_CHECK(ctx);
+    }
+    return EMO_OK;
+}
+
+int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    MatchParams p;
+    p.cand = ctx->cand;
+    p.chunk = ctx->chunk;
+    p.n_chunks = ctx->n_chunks;
+    p.chunks_per_split = ctx->n_chunks;
+    p.src = src;
+    p.W = W;
+    p.dim = ctx->dim;
+    p.bw = W / ctx->dim;
+    p.Q = p.bw * (H / ctx->dim);
+    p.mirrored = ctx->N != 1;
+    p.item = item;
+    p.dist = dist;
+    p.keys = nullptr;
+    const uint32_t Q = p.Q;
+    const bool big = Q >= (uint32_t)ctx->sm_count * 2048u * 2u;
+    switch (ctx->words) {
+        case 1: return big ? launch_match_t<1, 8, 256>(ctx, p, Q) : launch_match_t<1, 2, 128>(ctx, p, Q);
+        case 3: return big ? launch_match_t<3, 8, 256>(ctx, p, Q) : launch_match_t<3, 2, 128>(ctx, p, Q);
+        case 7: return launch_match_t<7, 2, 128>(ctx, p, Q);
+        case 12: return launch_match_t<12, 2, 128>(ctx, p, Q);
+    }
+    emo_set_error("match: unsupported vector length (words=%u)", ctx->words);
+    return EMO_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,71 @@
+// probe.cu — integer-pipe microbenchmark: the roofline denominator of the match kernel.
+// Every SM runs resident warps issuing independent chains of one instruction class; the result is
+// thread-level instructions per second (warp instructions x 32), measured with CUDA events.
+#include "common.cuh"
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed, int iters) {
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = seed * (threadIdx.x + 1) + i * 0x01020304u;
+        b[i] = seed ^ (0x9e3779b9u * (i + 1));
+    }
+    const uint32_t c = seed | 0x01010101u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (WHICH == 0) {
+                    a[i] = a[i] * c + b[i];  // IMAD
+                } else if (WHICH == 1) {
+                    a[i] = sad4(b[i], c, a[i]);  // VABSDIFF4.U8.ACC
+                } else if (WHICH == 2) {
+                    a[i] = min(a[i], min(b[i], c + a[(i + 1) & 7]));  // VIMNMX3 (+ one IADD feeding it)
+                } else {
+                    // the match inner loop: 4 x VABSDIFF4 + 2 x VIMNMX3 per (query, 4 candidates)
+                    const uint32_t d0 = sad4(b[i], c, 0), d1 = sad4(b[i], c + 1, 0), d2 = sad4(b[i], c + 2, 0),
+                                   d3 = sad4(b[i], c + 3, 0);
+                    a[i] = min(a[i], min(d0, d1));
+                    a[i] = min(a[i], min(d2, d3));
+                    b[i] += a[i];
+                }
+            }
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= a[i] + b[i];
+    if (r == 0x12345678u) out[0] = r;  // keep the chains alive
+}
+
+extern "C" int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s) {
+    EMO_REQUIRE(ctx && inst_per_s, EMO_ERR_ARG, "emo_probe_int_pipe: NULL argument");
+    EMO_REQUIRE(which >= 0 && which <= 3, EMO_ERR_ARG, "emo_probe_int_pipe: which must be 0..3");
+    EMO_CK(cudaSetDevice(ctx->device));
+    int rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], 256);
+    if (rc) return rc;
+    uint32_t *out = (uint32_t *)ctx->stage[1];
+    const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
+    // thread-level instructions per iteration of the measured class(es)
+    const double per_iter = which == 3 ? 4.0 * 8 * 6 : (which == 2 ? 4.0 * 8 * 2 : 4.0 * 8);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        EMO_CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+        switch (which) {
+            case 0: probe_kernel<0><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 1: probe_kernel<1><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 2: probe_kernel<2><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            default: probe_kernel<3><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+        }
+        EMO_LAUNCH_CHECK(ctx);
+        EMO_CK(cudaEventRecord(ctx->ev_stop, ctx->stream));
+        EMO_CK(cudaEventSynchronize(ctx->ev_stop));
+        float ms = 0;
+        EMO_CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *inst_per_s = per_iter * iters * (double)grid * block / (best * 1e-3);
+    return EMO_OK;
+}

@@ -1,0 +1,148 @@
+/*
+ * emosaic_cuda.h — C ABI of libemosaic_cuda.so, the B200 (sm_100a) implementation of
+ * emosaic's data-parallel core: tile analysis -> L1 nearest-colour match -> compose/tint.
+ *
+ * The reference (pepeiborra/emosaic, Rust) has no FFI seam; the three in-process calls this
+ * library replaces are cited on each entry point (paths relative to the reference root).
+ * Entry points are batch-granular: one call covers the whole tile library / source stripe,
+ * because a per-block call (the reference's closure granularity) cannot feed a GPU.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative emo_status;
+ *    the message of the last failure on the calling thread is emo_last_error().
+ *    Nothing unwinds across the boundary (the reference's panics/exit(1) become codes).
+ *  - one emo_ctx per GPU (one process per GPU under torchrun / one ctx per device in a
+ *    single process); a ctx is driven by one host thread at a time.
+ *  - `*_dev` variants take DEVICE pointers (same CUDA primary context, e.g. memory from
+ *    emo_dev_alloc or any CUDA allocator) and are asynchronous on the ctx stream;
+ *    the un-suffixed variants take HOST pointers, stage through the ctx's own device
+ *    buffers and are synchronous on return.
+ *  - images are row-major interleaved u8: RGB8 [H,W,3] or RGBA8 [H,W,4].
+ *  - item maps are int32, signed and 1-based like the reference's i16 ids
+ *    (tileset.rs:131-143): +k = tile k, -k = tile k mirrored horizontally, 0 never occurs.
+ *  - there is NO CPU fallback: without a usable CUDA device emo_create fails.
+ */
+#ifndef EMOSAIC_CUDA_H
+#define EMOSAIC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMO_ABI_VERSION 1
+
+typedef struct emo_ctx emo_ctx;
+
+typedef enum emo_status {
+    EMO_OK = 0,
+    EMO_ERR_ARG = -1,         /* bad argument (null pointer, size rule violated, item out of range) */
+    EMO_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    EMO_ERR_OOM = -3,         /* device or pinned-host allocation failed */
+    EMO_ERR_STATE = -4,       /* call sequence error (e.g. match before set_library) */
+    EMO_ERR_UNSUPPORTED = -5, /* valid in the reference but not implemented by this build */
+    EMO_ERR_NO_DEVICE = -6    /* no CUDA device / wrong architecture: there is no CPU path */
+} emo_status;
+
+int emo_abi_version(void);
+const char *emo_last_error(void);
+
+/* ---- context -------------------------------------------------------------------------- */
+/* Creates the per-GPU context (stream, scratch buffers). device = CUDA ordinal. */
+int emo_create(int device, emo_ctx **out);
+void emo_destroy(emo_ctx *ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work; NULL
+ * restores the ctx's own stream. */
+int emo_set_stream(emo_ctx *ctx, void *cuda_stream);
+int emo_sync(emo_ctx *ctx);
+/* Device name / SM count / compute capability of the ctx's GPU. */
+int emo_device_info(emo_ctx *ctx, char *name, size_t name_cap, int *sm_count, int *cc_major, int *cc_minor);
+/* Number of kernel launches issued by this ctx since creation (bench bookkeeping). */
+uint64_t emo_launch_count(emo_ctx *ctx);
+
+/* CUDA-event stopwatch on the ctx's current stream. */
+int emo_timer_start(emo_ctx *ctx);
+int emo_timer_stop(emo_ctx *ctx, float *elapsed_ms); /* synchronises the stop event */
+/* Numbered event marks on the ctx's current stream (slot < 65536), for per-kernel timing inside a
+ * longer timed region: emo_mark records, emo_mark_elapsed waits for mark b and returns b - a. */
+int emo_mark(emo_ctx *ctx, uint32_t slot);
+int emo_mark_elapsed(emo_ctx *ctx, uint32_t a, uint32_t b, float *elapsed_ms);
+
+/* Raw memory helpers so a host without its own CUDA bindings can keep data resident. */
+int emo_dev_alloc(emo_ctx *ctx, size_t bytes, void **out);
+int emo_dev_free(emo_ctx *ctx, void *p);
+int emo_host_alloc(emo_ctx *ctx, size_t bytes, void **out); /* pinned */
+int emo_host_free(emo_ctx *ctx, void *p);
+int emo_copy_h2d(emo_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
+int emo_copy_d2h(emo_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */
+
+/* ---- (1) tile analysis ------------------------------------------------------------------
+ * Replaces analyse::<N>() (src/mosaic/analysis.rs:5-20) + average_color()
+ * (src/mosaic/color.rs:14-42) looped over the library (src/main.rs:786-794).
+ * tiles [T,ts,ts,3] -> out [T,dim*dim,3]; cell = floor(ts/dim) square, cells row-major,
+ * per channel floor(sum/count) in integer arithmetic (bit-exact). dim=1 is "1to1",
+ * dim=2 is "4to1".  Requires 1 <= dim <= ts <= 4096. */
+int emo_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out);
+int emo_analyse_dev(emo_ctx *ctx, const uint8_t *tiles_dev, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out_dev);
+/* One pass over the tiles producing both the 1to1 ([T,1,3]) and 4to1 ([T,4,3]) analyses
+ * (what `-f` needs when both .emosaic_1to1 and .emosaic_4to1 are rebuilt). ts must be even. */
+int emo_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4);
+int emo_analyse_fused_dev(emo_ctx *ctx, const uint8_t *tiles_dev, uint64_t T, uint32_t ts, uint8_t *out1_dev,
+                          uint8_t *out4_dev);
+
+/* ---- (2) library / search set -----------------------------------------------------------
+ * Replaces TileSet::build_kiddo() (src/mosaic/tiles/tileset.rs:178-190) + Tile::coords()
+ * (tiles/tile.rs:106-119) + flipped_coords() (tiles/utils.rs:18-43): every tile enters the
+ * candidate set twice, (coords,+idx) then (mirror(coords),-idx), idx = position+1.
+ * colors [T,N,3] (N = dim*dim analysis cells), tile_px [T,ts,ts,3] (may be NULL if only
+ * emo_match is used).  The library stays resident on the GPU until replaced.
+ * The reference's i16 limit (T <= 32767, tileset.rs:182) does not apply: T < 2^30. */
+int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts);
+int emo_set_library_dev(emo_ctx *ctx, const uint8_t *colors_dev, const uint8_t *tile_px_dev, uint32_t T, uint32_t N,
+                        uint32_t ts);
+
+/* ---- (3) nearest-colour match -----------------------------------------------------------
+ * Replaces the get_tile closure of render_nto1 (src/mosaic/rendering.rs:158-221):
+ * get_img_colors (analysis.rs:23-36) -> coords -> KdTree::nearest_one::<Manhattan>
+ * (rendering.rs:187-195) for every dim x dim block of src [H,W,3].
+ * item/dist are [H/dim, W/dim] row-major; dist = L1 distance (sum |q-c| over 3N bytes);
+ * ties: smallest idx, unflipped before flipped (kiddo's leaf-scan order).
+ * W and H must be multiples of dim (main.rs:603-611). A source stripe (a contiguous range
+ * of block rows) is just a smaller image, which is how multi-GPU runs shard the work. */
+int emo_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);
+int emo_match_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, int32_t *item_dev,
+                  uint32_t *dist_dev);
+
+/* ---- (4) compose (+tint) -----------------------------------------------------------------
+ * Replaces render() (src/mosaic/rendering.rs:51-101) + TileSet::get_image()
+ * (tiles/tileset.rs:146-161) and, when out_channels == 4, the tint block
+ * (src/main.rs:447-478: alpha overlay of the nearest-resized source, image 0.25.2
+ * Rgba::blend in f32, bit-exact).
+ * item [H/dim,W/dim] -> out [H/dim*ts, W/dim*ts, out_channels].
+ *   out_channels == 3: RGB mosaic, src/tint_alpha ignored (src may be NULL)
+ *   out_channels == 4: RGBA = blend(mosaic, src upscaled, alpha = tint_alpha); alpha byte as
+ *                      the reference computes it. tint_alpha = (255*opacity) as u8. */
+int emo_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t W, uint32_t H,
+                uint32_t out_channels, uint8_t tint_alpha, uint8_t *out);
+int emo_compose_dev(emo_ctx *ctx, const int32_t *item_dev, const uint8_t *src_dev, uint32_t W, uint32_t H,
+                    uint32_t out_channels, uint8_t tint_alpha, uint8_t *out_dev);
+
+/* ---- whole path, host buffers ------------------------------------------------------------
+ * render_nto1 (+ tint) in one call: H2D(src) -> match -> compose -> D2H(out) with the copies
+ * pipelined against the kernels in block-row chunks. item/dist may be NULL. */
+int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t out_channels,
+               uint8_t tint_alpha, int32_t *item, uint32_t *dist, uint8_t *out);
+
+/* ---- measurement helpers ------------------------------------------------------------------
+ * Integer-pipe microbenchmark used as the roofline denominator of the match kernel:
+ * dependent-free streams of VABSDIFF4 / VIMNMX3 / IMAD on every SM.
+ * which: 0 = scalar INT32 (IMAD), 1 = VABSDIFF4.ACC, 2 = VIMNMX3, 3 = the match inner-loop mix
+ * (4 VABSDIFF4 + 2 VIMNMX3).  Returns thread-level instructions per second. */
+int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMOSAIC_CUDA_H */

@@ -1,0 +1,492 @@
+/*
+ * emosaic_oracle.c — CPU restatement of the pepeiborra/emosaic hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA
+ * product in emosaic_b200/csrc/.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * never links, imports or calls anything in oracle/.
+ *
+ * The reference is a Rust crate that cannot be built in this image (no
+ * cargo/rustc, needs nightly + 214 un-vendored crates), so this is a
+ * restatement, function by function, of the reference sources cited below
+ * (paths under /root/reference).  Arithmetic that lives in un-vendored crates
+ * (kiddo 4.2.0 nearest_one/Manhattan, image 0.25.2 Rgba::blend / resize
+ * Nearest / imageops::replace, bincode 1.3.3) is restated from the published
+ * algorithms of those pinned versions.
+ *
+ * Parity pinning: every known-answer vector the reference's own unit tests
+ * hold for this path (color.rs:49-72, analysis.rs:44-71, tile.rs:127-140,
+ * utils.rs:302-308, mod.rs:83-161) is checked in tests/test_oracle_kat.py.
+ * The argmin tie-break for > 320 tiles, the non-zero distance values, the
+ * f32 tint blend and the cache byte layout have NO reference test or golden
+ * vector: for those this oracle is "parity unpinned" (see DESIGN.md).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_OK 0
+#define ORC_ERR_EMPTY_RECT (-1)   /* color.rs:18 "Rectangle dimensions must be positive" */
+#define ORC_ERR_RECT_WIDTH (-2)   /* color.rs:19 "Rectangle extends beyond image width" */
+#define ORC_ERR_RECT_HEIGHT (-3)  /* color.rs:20 "Rectangle extends beyond image height" */
+#define ORC_ERR_ARG (-4)
+#define ORC_ERR_ZERO_ITEM (-5)    /* rendering.rs:198-203 assert closest.item != 0 */
+
+static uint32_t isqrt_u32(uint32_t n) {
+    uint32_t r = (uint32_t)floor(sqrt((double)n));
+    while ((uint64_t)r * r > n) r--;
+    while ((uint64_t)(r + 1) * (r + 1) <= n) r++;
+    return r;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---- color.rs:14-42  average_color ------------------------------------- */
+int orc_average_color(const uint8_t *img, uint32_t img_w, uint32_t img_h,
+                      uint32_t left, uint32_t top, uint32_t width, uint32_t height,
+                      uint8_t out[3]) {
+    if (!(width > 0 && height > 0)) return ORC_ERR_EMPTY_RECT;
+    if (!(left + width <= img_w)) return ORC_ERR_RECT_WIDTH;
+    if (!(top + height <= img_h)) return ORC_ERR_RECT_HEIGHT;
+    uint64_t r = 0, g = 0, b = 0;
+    for (uint32_t y = top; y < top + height; y++) {
+        const uint8_t *row = img + ((size_t)y * img_w + left) * 3;
+        for (uint32_t x = 0; x < width; x++) {
+            r += row[3 * x];
+            g += row[3 * x + 1];
+            b += row[3 * x + 2];
+        }
+    }
+    uint64_t n = (uint64_t)(width * height); /* color.rs:36 u64::from(width*height) */
+    out[0] = (uint8_t)(r / n);
+    out[1] = (uint8_t)(g / n);
+    out[2] = (uint8_t)(b / n);
+    return ORC_OK;
+}
+
+/* ---- analysis.rs:5-20  analyse::<N> ------------------------------------ */
+/* img is [h,w,3]; N = dim*dim cells, row-major; cell = floor(w/dim) x floor(h/dim). */
+int orc_analyse(const uint8_t *img, uint32_t w, uint32_t h, uint32_t N, uint8_t *out /*[N*3]*/) {
+    double dim = sqrt((double)N);
+    uint32_t dim_w = (uint32_t)floor((double)w / dim);
+    uint32_t dim_h = (uint32_t)floor((double)h / dim);
+    uint32_t d = (uint32_t)dim; /* `dim as usize` */
+    if (d == 0) return ORC_ERR_ARG;
+    for (uint32_t i = 0; i < N; i++) {
+        uint32_t top = i / d, left = i % d;
+        int rc = orc_average_color(img, w, h, left * dim_w, top * dim_h, dim_w, dim_h, out + 3 * i);
+        if (rc) return rc;
+    }
+    return ORC_OK;
+}
+
+/* Whole library: tiles [T,ts,ts,3] -> out [T,N,3].  main.rs:786-794 loops
+ * analyse() over the tiles sequentially; OpenMP here only speeds up the checker. */
+int orc_analyse_tiles(const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t N, uint8_t *out) {
+    int err = 0;
+    #pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < (int64_t)T; t++) {
+        int rc = orc_analyse(tiles + (size_t)t * ts * ts * 3, ts, ts, N, out + (size_t)t * N * 3);
+        if (rc) {
+            #pragma omp atomic write
+            err = rc;
+        }
+    }
+    return err;
+}
+
+/* ---- analysis.rs:23-36  get_img_colors::<N> ----------------------------- */
+void orc_get_img_colors(const uint8_t *src, uint32_t W, uint32_t x, uint32_t y, uint32_t step,
+                        uint32_t N, uint8_t *out /*[N*3]*/) {
+    for (uint32_t i = 0; i < N; i++) {
+        uint32_t xx = x + (i % step), yy = y + (i / step);
+        memcpy(out + 3 * i, src + ((size_t)yy * W + xx) * 3, 3);
+    }
+}
+
+/* ---- tiles/utils.rs:18-43  flipped_coords ------------------------------- */
+/* coords has D = 3N entries; rows = isqrt(D/3); swap cell j <-> cols-1-j in each cell-row. */
+void orc_flipped_coords_u8(uint8_t *coords, uint32_t D) {
+    uint32_t rows = isqrt_u32(D / 3), cols = rows, cir = cols * 3;
+    for (uint32_t i = 0; i < rows; i++)
+        for (uint32_t j = 0; j < cols / 2; j++) {
+            uint32_t a = i * cir + j * 3, b = (i + 1) * cir - (j + 1) * 3;
+            for (uint32_t h = 0; h < 3; h++) {
+                uint8_t t = coords[a + h]; coords[a + h] = coords[b + h]; coords[b + h] = t;
+            }
+        }
+}
+void orc_flipped_coords_u32(uint32_t *coords, uint32_t D) {
+    uint32_t rows = isqrt_u32(D / 3), cols = rows, cir = cols * 3;
+    for (uint32_t i = 0; i < rows; i++)
+        for (uint32_t j = 0; j < cols / 2; j++) {
+            uint32_t a = i * cir + j * 3, b = (i + 1) * cir - (j + 1) * 3;
+            for (uint32_t h = 0; h < 3; h++) {
+                uint32_t t = coords[a + h]; coords[a + h] = coords[b + h]; coords[b + h] = t;
+            }
+        }
+}
+
+/* ---- tiles/tile.rs:106-119  Tile::coords -------------------------------- */
+/* [N,3] u8 -> [3N] FixedU32<U0> (== plain u32), interleaved r,g,b; mirrored if flipped. */
+void orc_coords(const uint8_t *colors, uint32_t N, int flipped, uint32_t *out /*[3N]*/) {
+    for (uint32_t i = 0; i < N; i++) {
+        out[3 * i] = colors[3 * i];
+        out[3 * i + 1] = colors[3 * i + 1];
+        out[3 * i + 2] = colors[3 * i + 2];
+    }
+    if (flipped) orc_flipped_coords_u32(out, 3 * N);
+}
+
+/* ---- tileset.rs:178-190 build_kiddo + rendering.rs:187-195 nearest_one --- */
+/* Candidate set in insertion order: (coords(t), +idx), (mirror(coords(t)), -idx), idx = t+1.
+ * kiddo 4.2.0 fixed::KdTree::nearest_one::<Manhattan>: L1 distance in u32, a leaf is
+ * scanned in storage order and the best is replaced only on strict `<`; the initial best
+ * is (distance = max, item = 0).  With 2T <= 640 the tree is ONE leaf in insertion
+ * order, so the winner is: min distance, then smallest idx, then unflipped before
+ * flipped.  That rule is this oracle's canonical tie-break for every T (unpinned for
+ * T > 320, where kiddo's unstable select_nth decides the leaf order). */
+void orc_build_candidates(const uint8_t *colors /*[T,N,3]*/, uint32_t T, uint32_t N,
+                          uint8_t *cand /*[2T,3N]*/, int32_t *items /*[2T]*/) {
+    uint32_t D = 3 * N;
+    for (uint32_t t = 0; t < T; t++) {
+        uint8_t *a = cand + (size_t)(2 * t) * D, *b = a + D;
+        memcpy(a, colors + (size_t)t * D, D);
+        memcpy(b, a, D);
+        orc_flipped_coords_u8(b, D);
+        items[2 * t] = (int32_t)(t + 1);
+        items[2 * t + 1] = -(int32_t)(t + 1);
+    }
+}
+
+static inline uint32_t l1_u8(const uint8_t *a, const uint8_t *b, uint32_t D) {
+    uint32_t s = 0;
+    for (uint32_t d = 0; d < D; d++) s += (uint32_t)abs((int)a[d] - (int)b[d]);
+    return s;
+}
+
+/* One query against the candidate list in insertion order, strict `<`. */
+int orc_nearest_one(const uint8_t *cand, const int32_t *items, uint32_t L, uint32_t D,
+                    const uint8_t *q, int32_t *item, uint32_t *dist) {
+    uint32_t best = UINT32_MAX; int32_t bi = 0;
+    for (uint32_t c = 0; c < L; c++) {
+        uint32_t s = l1_u8(cand + (size_t)c * D, q, D);
+        if (s < best) { best = s; bi = items[c]; }
+    }
+    *item = bi; *dist = best;
+    return bi == 0 ? ORC_ERR_ZERO_ITEM : ORC_OK;
+}
+
+/* rendering.rs:124-230 render_nto1 matching stage (no_repeat=false, randomize=None):
+ * for every block (x,y) of the source, query = get_img_colors, answer = nearest_one.
+ * item/dist are [H/dim, W/dim] row-major (block-row major). Brute force. */
+int orc_match(const uint8_t *colors, uint32_t T, uint32_t N,
+              const uint8_t *src, uint32_t W, uint32_t H,
+              int32_t *item, uint32_t *dist) {
+    uint32_t dim = isqrt_u32(N), D = 3 * N;
+    if (dim * dim != N || dim == 0 || W % dim || H % dim) return ORC_ERR_ARG;
+    uint32_t L = 2 * T;
+    uint8_t *cand = (uint8_t *)malloc((size_t)L * D + 1);
+    int32_t *items = (int32_t *)malloc((size_t)L * sizeof(int32_t) + 4);
+    orc_build_candidates(colors, T, N, cand, items);
+    uint32_t bw = W / dim, bh = H / dim;
+    int err = 0;
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t by = 0; by < (int64_t)bh; by++) {
+        uint8_t *q = (uint8_t *)malloc(D);
+        for (uint32_t bx = 0; bx < bw; bx++) {
+            orc_get_img_colors(src, W, bx * dim, (uint32_t)by * dim, dim, N, q);
+            int rc = orc_nearest_one(cand, items, L, D, q, &item[by * bw + bx], &dist[by * bw + bx]);
+            if (rc) {
+                #pragma omp atomic write
+                err = rc;
+            }
+        }
+        free(q);
+    }
+    free(cand); free(items);
+    return err;
+}
+
+/* ---- bucketed KD-tree, L1, leaf capacity 640 ---------------------------- */
+/* The reference's algorithm class (kiddo KdTree<_, i16, 3N, 640, u16> + nearest_one),
+ * restated with the canonical tie-break so its answers equal orc_match exactly:
+ * a subtree is pruned only when its L1 lower bound is strictly greater than the
+ * current best distance, and inside a leaf (dist, rank) is compared lexicographically.
+ * Used (a) to cross-check the brute-force oracle on large cases and (b) as the timed
+ * "reference-algorithm" CPU baseline.  It is NOT kiddo's exact tree layout. */
+typedef struct {
+    int32_t left, right;      /* children (node ids) or -1 */
+    uint32_t dimn;            /* split dimension */
+    uint32_t split;           /* points with v[dimn] < split go left */
+    uint32_t start, count;    /* leaf: range in perm */
+} kd_node;
+
+typedef struct {
+    uint32_t D, L;
+    uint8_t *pts;             /* [L,D] permuted copy for locality */
+    uint32_t *rank;           /* [L] insertion rank of each permuted point */
+    kd_node *nodes;
+    uint32_t n_nodes, cap_nodes;
+} kd_tree;
+
+static uint32_t kd_new_node(kd_tree *t) {
+    if (t->n_nodes == t->cap_nodes) {
+        t->cap_nodes = t->cap_nodes ? t->cap_nodes * 2 : 64;
+        t->nodes = (kd_node *)realloc(t->nodes, t->cap_nodes * sizeof(kd_node));
+    }
+    kd_node *n = &t->nodes[t->n_nodes];
+    n->left = n->right = -1; n->dimn = 0; n->split = 0; n->start = n->count = 0;
+    return t->n_nodes++;
+}
+
+typedef struct { const uint8_t *base; uint32_t D, dimn; } kd_cmp_ctx;
+static kd_cmp_ctx g_cmp; /* build is single-threaded */
+static int kd_cmp(const void *a, const void *b) {
+    uint32_t ia = *(const uint32_t *)a, ib = *(const uint32_t *)b;
+    uint8_t va = g_cmp.base[(size_t)ia * g_cmp.D + g_cmp.dimn], vb = g_cmp.base[(size_t)ib * g_cmp.D + g_cmp.dimn];
+    if (va != vb) return va < vb ? -1 : 1;
+    return ia < ib ? -1 : (ia > ib);
+}
+
+static uint32_t kd_build_rec(kd_tree *t, const uint8_t *cand, uint32_t *idx, uint32_t start,
+                             uint32_t count, uint32_t depth, uint32_t bucket) {
+    uint32_t id = kd_new_node(t);
+    if (count <= bucket) { t->nodes[id].start = start; t->nodes[id].count = count; return id; }
+    /* choose the next dimension (cycling like kiddo) that actually separates the points */
+    for (uint32_t tries = 0; tries < t->D; tries++) {
+        uint32_t dimn = (depth + tries) % t->D;
+        g_cmp.base = cand; g_cmp.D = t->D; g_cmp.dimn = dimn;
+        qsort(idx + start, count, sizeof(uint32_t), kd_cmp);
+        uint32_t mid = count / 2;
+        uint8_t sv = cand[(size_t)idx[start + mid] * t->D + dimn];
+        /* move the pivot to the start of the run of equal values (all == sv go right) */
+        while (mid > 0 && cand[(size_t)idx[start + mid - 1] * t->D + dimn] == sv) mid--;
+        if (mid == 0) {
+            /* try the first value greater than sv instead */
+            mid = count / 2;
+            while (mid < count && cand[(size_t)idx[start + mid] * t->D + dimn] == sv) mid++;
+            if (mid == count) continue; /* all equal on this dim */
+            sv = cand[(size_t)idx[start + mid] * t->D + dimn];
+        }
+        uint32_t l = kd_build_rec(t, cand, idx, start, mid, depth + tries + 1, bucket);
+        uint32_t r = kd_build_rec(t, cand, idx, start + mid, count - mid, depth + tries + 1, bucket);
+        kd_node *n = &t->nodes[id];
+        n->left = (int32_t)l; n->right = (int32_t)r; n->dimn = dimn; n->split = sv;
+        return id;
+    }
+    /* all points identical: oversized leaf */
+    t->nodes[id].start = start; t->nodes[id].count = count;
+    return id;
+}
+
+void *orc_kd_build(const uint8_t *cand /*[L,D]*/, uint32_t L, uint32_t D, uint32_t bucket) {
+    kd_tree *t = (kd_tree *)calloc(1, sizeof(kd_tree));
+    t->D = D; t->L = L;
+    uint32_t *idx = (uint32_t *)malloc((size_t)(L + 1) * sizeof(uint32_t));
+    for (uint32_t i = 0; i < L; i++) idx[i] = i;
+    kd_build_rec(t, cand, idx, 0, L, 0, bucket ? bucket : 640);
+    t->pts = (uint8_t *)malloc((size_t)L * D + 1);
+    t->rank = idx;
+    for (uint32_t i = 0; i < L; i++) memcpy(t->pts + (size_t)i * D, cand + (size_t)idx[i] * D, D);
+    return t;
+}
+
+void orc_kd_free(void *h) {
+    kd_tree *t = (kd_tree *)h;
+    if (!t) return;
+    free(t->pts); free(t->rank); free(t->nodes); free(t);
+}
+
+static void kd_query_rec(const kd_tree *t, uint32_t id, const uint8_t *q, uint32_t *off,
+                         uint32_t rd, uint32_t *best, uint32_t *brank) {
+    const kd_node *n = &t->nodes[id];
+    if (n->left < 0) {
+        const uint8_t *p = t->pts + (size_t)n->start * t->D;
+        for (uint32_t i = 0; i < n->count; i++, p += t->D) {
+            uint32_t s = l1_u8(p, q, t->D), r = t->rank[n->start + i];
+            if (s < *best || (s == *best && r < *brank)) { *best = s; *brank = r; }
+        }
+        return;
+    }
+    uint32_t dimn = n->dimn, qv = q[dimn];
+    int is_left = qv < n->split;
+    uint32_t closer = is_left ? (uint32_t)n->left : (uint32_t)n->right;
+    uint32_t further = is_left ? (uint32_t)n->right : (uint32_t)n->left;
+    kd_query_rec(t, closer, q, off, rd, best, brank);
+    /* distance from q to the far half-space along dimn: left holds v < split, right v >= split */
+    uint32_t new_off = is_left ? (n->split - qv) : (qv - n->split + 1);
+    uint32_t old_off = off[dimn];
+    uint32_t nrd = rd - old_off + (new_off > old_off ? new_off : old_off);
+    if (nrd <= *best) {
+        uint32_t keep = off[dimn];
+        off[dimn] = new_off > old_off ? new_off : old_off;
+        kd_query_rec(t, further, q, off, nrd, best, brank);
+        off[dimn] = keep;
+    }
+}
+
+/* items convention: rank r -> item = +(r/2+1) if r even else -(r/2+1)  (tileset.rs:180-188) */
+int orc_match_kd(const void *h, const uint8_t *src, uint32_t W, uint32_t H, uint32_t N,
+                 int32_t *item, uint32_t *dist) {
+    const kd_tree *t = (const kd_tree *)h;
+    uint32_t dim = isqrt_u32(N), D = 3 * N;
+    if (dim * dim != N || D != t->D || W % dim || H % dim) return ORC_ERR_ARG;
+    uint32_t bw = W / dim, bh = H / dim;
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t by = 0; by < (int64_t)bh; by++) {
+        uint8_t *q = (uint8_t *)malloc(D);
+        uint32_t *off = (uint32_t *)calloc(D, sizeof(uint32_t));
+        for (uint32_t bx = 0; bx < bw; bx++) {
+            orc_get_img_colors(src, W, bx * dim, (uint32_t)by * dim, dim, N, q);
+            uint32_t best = UINT32_MAX, brank = UINT32_MAX;
+            kd_query_rec(t, 0, q, off, 0, &best, &brank);
+            dist[by * bw + bx] = best;
+            item[by * bw + bx] = (brank & 1) ? -(int32_t)(brank / 2 + 1) : (int32_t)(brank / 2 + 1);
+        }
+        free(q); free(off);
+    }
+    return ORC_OK;
+}
+
+/* ---- rendering.rs:51-101 render + tileset.rs:131-161 get_tile/get_image -- */
+/* out[by*ts + r][bx*ts + c] = tile[|item|-1][r][flipped ? ts-1-c : c]; out is
+ * [H/dim*ts, W/dim*ts, 3].  imageops::replace is a clipped row copy and
+ * flip_horizontal reverses pixels in each row (image 0.25.2); the strip/merge
+ * double copy of the reference is an implementation detail with the same result. */
+int orc_render(const uint8_t *tile_px /*[T,ts,ts,3]*/, uint32_t T, uint32_t ts,
+               const int32_t *item, uint32_t bw, uint32_t bh, uint8_t *out) {
+    size_t OW = (size_t)bw * ts;
+    int err = 0;
+    #pragma omp parallel for schedule(static)
+    for (int64_t by = 0; by < (int64_t)bh; by++) {
+        for (uint32_t bx = 0; bx < bw; bx++) {
+            int32_t it = item[by * bw + bx];
+            uint32_t a = (uint32_t)(it < 0 ? -it : it);
+            if (it == 0 || a > T) { err = ORC_ERR_ZERO_ITEM; continue; }
+            const uint8_t *tp = tile_px + (size_t)(a - 1) * ts * ts * 3;
+            for (uint32_t r = 0; r < ts; r++) {
+                uint8_t *o = out + (((size_t)by * ts + r) * OW + (size_t)bx * ts) * 3;
+                const uint8_t *trow = tp + (size_t)r * ts * 3;
+                if (it > 0) memcpy(o, trow, (size_t)ts * 3);
+                else for (uint32_t c = 0; c < ts; c++) memcpy(o + 3 * c, trow + 3 * (ts - 1 - c), 3);
+            }
+        }
+    }
+    return err;
+}
+
+/* ---- main.rs:447-478 tint block ----------------------------------------- */
+/* image 0.25.2 `impl Blend for Rgba<u8>` (src-over in f32, every op rounded
+ * individually, NumCast truncation), restated from the published source:
+ *   fg.a == 0   -> keep bg;   fg.a == 255 -> copy fg
+ *   bg_c = bg/255, fg_c = fg/255, bg_a = 255/255 = 1, fg_a = A/255
+ *   alpha_final = bg_a + fg_a - bg_a*fg_a
+ *   out_c = (fg_c*fg_a + (bg_c*bg_a)*(1-fg_a)) / alpha_final
+ *   result = trunc(255*out_c), alpha = trunc(255*alpha_final)
+ * Compile this file with -ffp-contract=off so no FMA is formed. */
+static inline void blend_px(const uint8_t bg[3], const uint8_t fg[3], uint8_t A, uint8_t out[4]) {
+    if (A == 0) { out[0] = bg[0]; out[1] = bg[1]; out[2] = bg[2]; out[3] = 255; return; }
+    if (A == 255) { out[0] = fg[0]; out[1] = fg[1]; out[2] = fg[2]; out[3] = 255; return; }
+    volatile float max_t = 255.0f;
+    float bg_a = 255.0f / max_t, fg_a = (float)A / max_t;
+    float alpha_final = bg_a + fg_a - bg_a * fg_a;
+    if (alpha_final == 0.0f) { out[0] = bg[0]; out[1] = bg[1]; out[2] = bg[2]; out[3] = 255; return; }
+    for (int c = 0; c < 3; c++) {
+        float b = (float)bg[c] / max_t, f = (float)fg[c] / max_t;
+        float b_a = b * bg_a, f_a = f * fg_a;
+        float o_a = f_a + b_a * (1.0f - fg_a);
+        float o = o_a / alpha_final;
+        out[c] = (uint8_t)(max_t * o);
+    }
+    out[3] = (uint8_t)(max_t * alpha_final);
+}
+
+void orc_blend_lut(uint8_t A, uint8_t *lut /*[256 bg][256 fg]*/, uint8_t *alpha_out) {
+    uint8_t o[4];
+    for (int bg = 0; bg < 256; bg++)
+        for (int fg = 0; fg < 256; fg++) {
+            uint8_t b[3] = {(uint8_t)bg, 0, 0}, f[3] = {(uint8_t)fg, 0, 0};
+            blend_px(b, f, A, o);
+            lut[bg * 256 + fg] = o[0];
+            *alpha_out = o[3];
+        }
+}
+
+/* alpha byte: main.rs:449 `(255.0 * tint_opacity) as u8` with tint_opacity: f64 (clap) */
+uint8_t orc_tint_alpha(double tint_opacity) {
+    double v = 255.0 * tint_opacity;
+    if (v != v || v <= 0.0) return 0;
+    if (v >= 255.0) return 255;
+    return (uint8_t)v; /* Rust `as u8` saturates and truncates */
+}
+
+/* mosaic [OH,OW,3] + source [H,W,3] -> RGBA [OH,OW,4].
+ * overlay pixel (X,Y) = src(floor((X+.5)*W/OW), floor((Y+.5)*H/OH)) — image 0.25.2
+ * resize(Nearest): box kernel with support 0 picks exactly that one source pixel. */
+void orc_tint(const uint8_t *mosaic, uint32_t OW, uint32_t OH, const uint8_t *src, uint32_t W,
+              uint32_t H, uint8_t A, uint8_t *out) {
+    float xr = (float)W / (float)OW, yr = (float)H / (float)OH;
+    #pragma omp parallel for schedule(static)
+    for (int64_t Y = 0; Y < (int64_t)OH; Y++) {
+        uint32_t sy = (uint32_t)floorf(((float)Y + 0.5f) * yr);
+        if (sy > H - 1) sy = H - 1;
+        for (uint32_t X = 0; X < OW; X++) {
+            uint32_t sx = (uint32_t)floorf(((float)X + 0.5f) * xr);
+            if (sx > W - 1) sx = W - 1;
+            blend_px(mosaic + ((size_t)Y * OW + X) * 3, src + ((size_t)sy * W + sx) * 3, A,
+                     out + ((size_t)Y * OW + X) * 4);
+        }
+    }
+}
+
+/* ---- main.rs:567-587 source dimension rule ------------------------------- */
+void orc_adjust_dims(uint32_t w, uint32_t h, uint32_t downsample, uint32_t dim, uint32_t *nw, uint32_t *nh) {
+    uint32_t a = w / downsample, b = h / downsample;
+    uint32_t m = a % dim;
+    if (m > dim / 2) a += dim - m; else a -= m;
+    m = b % dim;
+    if (m > dim / 2) b += dim - m; else b -= m;
+    *nw = a; *nh = b;
+}
+
+/* ---- cache: tile.rs:38-65, tileset.rs:28-75, bincode 1.3.3 defaults ------- */
+/* layout: u64 T | T x { u64 3N | 3N bytes | u16 idx | u8 tag [| u64 len | bytes] }
+ *         | u64 T | T x { u64 len | path bytes }.  All little-endian, fixint. */
+static void put_u64(uint8_t **p, uint64_t v) { for (int i = 0; i < 8; i++) *(*p)++ = (uint8_t)(v >> (8 * i)); }
+static void put_u16(uint8_t **p, uint16_t v) { *(*p)++ = (uint8_t)v; *(*p)++ = (uint8_t)(v >> 8); }
+
+/* dates[t] / paths[t] are NUL-terminated; dates[t] may be NULL (Option::None).
+ * Returns bytes needed; writes only if buf != NULL and cap suffices. */
+int64_t orc_cache_serialize(const uint8_t *colors, uint32_t T, uint32_t N, const uint16_t *idx,
+                            const char *const *dates, const char *const *paths,
+                            uint8_t *buf, uint64_t cap) {
+    uint64_t need = 8;
+    for (uint32_t t = 0; t < T; t++) need += 8 + 3 * (uint64_t)N + 2 + 1 + (dates && dates[t] ? 8 + strlen(dates[t]) : 0);
+    need += 8;
+    for (uint32_t t = 0; t < T; t++) need += 8 + strlen(paths[t]);
+    if (!buf) return (int64_t)need;
+    if (cap < need) return -1;
+    uint8_t *p = buf;
+    put_u64(&p, T);
+    for (uint32_t t = 0; t < T; t++) {
+        put_u64(&p, 3 * (uint64_t)N);
+        memcpy(p, colors + (size_t)t * 3 * N, 3 * N); p += 3 * N;
+        put_u16(&p, idx[t]);
+        if (dates && dates[t]) { *p++ = 1; uint64_t l = strlen(dates[t]); put_u64(&p, l); memcpy(p, dates[t], l); p += l; }
+        else *p++ = 0;
+    }
+    put_u64(&p, T);
+    for (uint32_t t = 0; t < T; t++) { uint64_t l = strlen(paths[t]); put_u64(&p, l); memcpy(p, paths[t], l); p += l; }
+    return (int64_t)(p - buf);
+}

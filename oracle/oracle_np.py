@@ -1,0 +1,107 @@
+"""Independent numpy restatement of the same reference functions (TEST INFRASTRUCTURE).
+
+Written separately from emosaic_oracle.c so the two can be cross-checked against each
+other and against the reference's own known-answer vectors.  Citations as in the C file.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def analyse(img: np.ndarray, N: int) -> np.ndarray:
+    """analysis.rs:5-20 + color.rs:14-42 (u64 sums, truncating division)."""
+    h, w = img.shape[:2]
+    dim = int(np.sqrt(N))
+    cw, ch = int(np.floor(w / np.sqrt(N))), int(np.floor(h / np.sqrt(N)))
+    assert cw > 0 and ch > 0, "Rectangle dimensions must be positive"
+    out = np.zeros((N, 3), np.uint8)
+    for i in range(N):
+        top, left = i // dim, i % dim
+        cell = img[top * ch:(top + 1) * ch, left * cw:(left + 1) * cw].astype(np.uint64)
+        out[i] = (cell.sum(axis=(0, 1)) // np.uint64(cw * ch)).astype(np.uint8)
+    return out
+
+
+def analyse_tiles(tiles: np.ndarray, N: int) -> np.ndarray:
+    T, ts = tiles.shape[:2]
+    dim = int(np.sqrt(N))
+    c = ts // dim
+    t = tiles[:, :dim * c, :dim * c].reshape(T, dim, c, dim, c, 3).astype(np.uint64)
+    return (t.sum(axis=(2, 4)) // np.uint64(c * c)).astype(np.uint8).reshape(T, N, 3)
+
+
+def queries(src: np.ndarray, N: int) -> np.ndarray:
+    """analysis.rs:23-36 for every block: [bh,bw,N*3], cells row-major inside the block."""
+    dim = int(np.sqrt(N))
+    H, W = src.shape[:2]
+    q = src.reshape(H // dim, dim, W // dim, dim, 3).transpose(0, 2, 1, 3, 4)
+    return np.ascontiguousarray(q).reshape(H // dim, W // dim, N * 3)
+
+
+def mirror(vecs: np.ndarray, N: int) -> np.ndarray:
+    """utils.rs:18-43 on [..., 3N] vectors."""
+    dim = int(np.sqrt(N))
+    v = vecs.reshape(vecs.shape[:-1] + (dim, dim, 3))
+    return np.ascontiguousarray(v[..., ::-1, :]).reshape(vecs.shape)
+
+
+def match(colors: np.ndarray, src: np.ndarray, chunk: int = 4096):
+    """tileset.rs:178-190 + rendering.rs:187-195 with the canonical tie-break."""
+    T, N = colors.shape[:2]
+    base = colors.reshape(T, 3 * N)
+    cand = np.empty((2 * T, 3 * N), np.int32)
+    cand[0::2] = base
+    cand[1::2] = mirror(base, N)
+    q = queries(src, N).astype(np.int32)
+    bh, bw = q.shape[:2]
+    qf = q.reshape(-1, 3 * N)
+    item = np.zeros(qf.shape[0], np.int32)
+    dist = np.zeros(qf.shape[0], np.uint32)
+    for s in range(0, qf.shape[0], chunk):
+        d = np.abs(qf[s:s + chunk, None, :] - cand[None, :, :]).sum(axis=2)
+        r = d.argmin(axis=1)  # first minimum == lowest insertion rank
+        dist[s:s + chunk] = d[np.arange(d.shape[0]), r]
+        item[s:s + chunk] = np.where(r % 2 == 0, r // 2 + 1, -(r // 2 + 1))
+    return item.reshape(bh, bw), dist.reshape(bh, bw)
+
+
+def render(tile_px: np.ndarray, item: np.ndarray) -> np.ndarray:
+    """rendering.rs:51-101."""
+    T, ts = tile_px.shape[:2]
+    bh, bw = item.shape
+    a = np.abs(item) - 1
+    px = tile_px[a]  # [bh,bw,ts,ts,3]
+    px = np.where((item < 0)[:, :, None, None, None], px[:, :, :, ::-1, :], px)
+    return np.ascontiguousarray(px.transpose(0, 2, 1, 3, 4)).reshape(bh * ts, bw * ts, 3)
+
+
+def blend(bg: np.ndarray, fg: np.ndarray, A: int):
+    """image 0.25.2 Rgba<u8>::blend with bg alpha 255 and fg alpha A. Returns (rgb, alpha_byte)."""
+    f = np.float32
+    if A == 0:
+        return bg.copy(), 255
+    if A == 255:
+        return fg.copy(), 255
+    m = f(255.0)
+    bga, fga = f(255.0) / m, f(A) / m
+    af = f(f(bga + fga) - f(bga * fga))
+    b = bg.astype(np.float32) / m
+    g = fg.astype(np.float32) / m
+    o = ((g * fga).astype(np.float32) + ((b * bga).astype(np.float32) * f(f(1.0) - fga)).astype(np.float32)).astype(np.float32)
+    o = (o / af).astype(np.float32)
+    return np.trunc((m * o).astype(np.float32)).astype(np.uint8), int(np.trunc(m * af))
+
+
+def tint(mosaic: np.ndarray, src: np.ndarray, A: int) -> np.ndarray:
+    """main.rs:447-478."""
+    OH, OW = mosaic.shape[:2]
+    H, W = src.shape[:2]
+    f = np.float32
+    sx = np.minimum(np.floor((np.arange(OW, dtype=np.float32) + f(0.5)) * (f(W) / f(OW))).astype(np.int64), W - 1)
+    sy = np.minimum(np.floor((np.arange(OH, dtype=np.float32) + f(0.5)) * (f(H) / f(OH))).astype(np.int64), H - 1)
+    fg = src[sy][:, sx]
+    rgb, a = blend(mosaic, fg, A)
+    out = np.empty((OH, OW, 4), np.uint8)
+    out[..., :3] = rgb
+    out[..., 3] = a
+    return out

@@ -1,0 +1,327 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI.  Needs a B200 (-m gpu).
+
+Bit-exact everywhere: the path is integer/byte arithmetic, and the f32 tint blend is reproduced
+exactly (tolerance 0)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import emosaic_b200 as emo
+import oracle
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---- analysis ------------------------------------------------------------------------------------
+def test_reference_kat_average(ctx):
+    # color.rs:49-64 through the kernel: a 2x2 tile analysed with N=1
+    img = np.array([[[100, 150, 200], [200, 100, 50]], [[50, 200, 100], [150, 50, 150]]], np.uint8)
+    assert emo.analyse(img, 1, ctx).tolist() == [[125, 125, 125]]
+    # analysis.rs:44-55
+    red = np.zeros((2, 2, 3), np.uint8)
+    red[..., 0] = 255
+    assert emo.analyse(red, 4, ctx).tolist() == [[255, 0, 0]] * 4
+
+
+@pytest.mark.parametrize("ts,dim,T", [(64, 1, 301), (64, 2, 301), (32, 1, 1000), (32, 2, 1000), (16, 1, 77), (16, 2, 77),
+                                      (8, 1, 50), (8, 2, 50), (12, 3, 40), (16, 4, 33), (10, 3, 21), (7, 2, 19), (5, 5, 9),
+                                      (1, 1, 5), (128, 2, 6)])
+def test_analyse_parity(ctx, ts, dim, T):
+    rng = np.random.default_rng(ts * 100 + dim)
+    tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    tiles[0] = 255  # saturated sums
+    tiles[1] = 0
+    got = ctx.analyse_tiles(tiles, dim)
+    assert (got == oracle.analyse_tiles(tiles, dim * dim)).all()
+
+
+@pytest.mark.parametrize("ts,T", [(64, 4099), (32, 5000), (16, 100), (6, 10)])
+def test_analyse_fused_parity(ctx, ts, T):
+    rng = np.random.default_rng(ts)
+    tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    o1, o4 = ctx.analyse_tiles_fused(tiles)
+    assert (o1 == oracle.analyse_tiles(tiles, 1)).all()
+    assert (o4 == oracle.analyse_tiles(tiles, 4)).all()
+
+
+def test_analyse_errors(ctx):
+    tiles = np.zeros((2, 4, 4, 3), np.uint8)
+    with pytest.raises(emo.EmosaicError, match="Rectangle dimensions must be positive"):
+        ctx.analyse_tiles(tiles, 5)  # floor(4/5) == 0 -> color.rs:18 panic
+    assert ctx.analyse_tiles(np.zeros((0, 8, 8, 3), np.uint8), 2).shape == (0, 4, 3)  # empty library
+    with pytest.raises(emo.EmosaicError, match="divisible by 2"):
+        ctx.analyse_tiles_fused(np.zeros((2, 5, 5, 3), np.uint8))
+
+
+def test_analyse_full_size_properties(ctx):
+    """C3 geometry at a size the box handles in seconds: 200k tiles of 64x64 generated on the host in
+    slabs; property: the 1to1 mean is bounded by the 4to1 quadrant means and both equal the oracle on a
+    sampled subset."""
+    T = 200_000
+    rng = np.random.default_rng(1234)
+    tiles = rng.integers(0, 256, (T, 64, 64, 3), dtype=np.uint8)
+    o1, o4 = ctx.analyse_tiles_fused(tiles)
+    sel = rng.choice(T, 4096, replace=False)
+    assert (o1[sel] == oracle.analyse_tiles(tiles[sel], 1)).all()
+    assert (o4[sel] == oracle.analyse_tiles(tiles[sel], 4)).all()
+    q = o4.astype(np.int64)
+    lo, hi = q.min(1), q.max(1)
+    assert ((o1[:, 0] >= lo) & (o1[:, 0] <= hi)).all()
+    # exact identity: floor(total/4096) with total = sum of quadrant sums; check via uint64 numpy on all tiles
+    tot = tiles.reshape(T, -1, 3).sum(1, dtype=np.uint64) // np.uint64(4096)
+    assert (o1[:, 0] == tot.astype(np.uint8)).all()
+
+
+# ---- match ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,T,H,W", [(1, 300, 100, 100), (1, 4096, 100, 100), (1, 1, 3, 5), (1, 17, 1, 1), (4, 500, 64, 96),
+                                     (4, 10000, 128, 128), (9, 200, 30, 42), (16, 100, 16, 24), (1, 33000, 64, 64),
+                                     (4, 20, 2, 2), (1, 2500, 700, 900)])
+def test_match_parity(ctx, N, T, H, W):
+    rng = np.random.default_rng(N * 1000 + T)
+    colors = rng.integers(0, 256, (T, N, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ctx.set_library(colors)
+    item, dist = ctx.match(src)
+    if T * H * W <= 3e9:
+        ri, rd = oracle.match(colors, src)
+    else:
+        ri, rd = oracle.KdTree(colors).match(src)
+    assert (dist == rd).all()
+    assert (item == ri).all()
+
+
+def test_match_ties_and_duplicates(ctx):
+    # heavy exact ties: 8-colour palette, many duplicate tiles; the canonical winner is the smallest idx
+    g = np.load(os.path.join(GOLD, "ties_palette.npz"))
+    ctx.set_library(g["colors"])
+    item, dist = ctx.match(g["src"])
+    assert (item == g["item"]).all() and (dist == g["dist"]).all() and (dist == 0).all()
+    # all tiles identical: always +1
+    colors = np.full((1000, 4, 3), 77, np.uint8)
+    ctx.set_library(colors)
+    item, dist = ctx.match(np.random.default_rng(0).integers(0, 256, (32, 32, 3), dtype=np.uint8))
+    assert (item == 1).all()
+    # quantised colours (multiples of 32): ties between distinct tiles at non-zero distance
+    rng = np.random.default_rng(11)
+    colors = (rng.integers(0, 8, (5000, 1, 3)) * 32).astype(np.uint8)
+    src = (rng.integers(0, 8, (96, 96, 3)) * 32 + 5).astype(np.uint8)
+    ctx.set_library(colors)
+    item, dist = ctx.match(src)
+    ri, rd = oracle.match(colors, src)
+    assert (item == ri).all() and (dist == rd).all()
+
+
+def test_match_mirror_sign(ctx):
+    asym = np.array([[[1, 1, 1], [200, 200, 200], [1, 1, 1], [200, 200, 200]]], np.uint8)
+    q = np.array([[[200, 200, 200], [1, 1, 1]], [[200, 200, 200], [1, 1, 1]]], np.uint8)
+    ctx.set_library(asym)
+    item, dist = ctx.match(q)
+    assert item.tolist() == [[-1]] and dist.tolist() == [[0]]
+    item, dist = ctx.match(q[:, ::-1].copy())
+    assert item.tolist() == [[1]] and dist.tolist() == [[0]]
+
+
+def test_match_errors(ctx):
+    ctx.set_library(np.zeros((3, 4, 3), np.uint8))
+    with pytest.raises(emo.EmosaicError, match="Dimensions must be divisible by 2"):
+        ctx.match(np.zeros((5, 4, 3), np.uint8))
+    with pytest.raises(emo.EmosaicError, match="not a square"):
+        ctx.set_library(np.zeros((3, 5, 3), np.uint8))
+    with pytest.raises(emo.EmosaicError):  # N=25 (--mode 5) not built yet: loud, not silent
+        ctx.set_library(np.zeros((3, 25, 3), np.uint8))
+    c2 = emo.Context(0)
+    with pytest.raises(emo.EmosaicError, match="no library"):
+        c2.match(np.zeros((4, 4, 3), np.uint8))
+    c2.close()
+
+
+# ---- the reference's end-to-end universe test (mod.rs:83-161) through the CUDA path ------------------
+@pytest.mark.parametrize("N", [1, 4, 9])
+def test_universe_roundtrip(ctx, N):
+    from test_oracle_kat import universe
+    dim = int(N ** 0.5)
+    uni = universe(N)
+    ts = emo.TileSet(N=N)
+    colors = ctx.analyse_tiles(uni, dim)
+    for i, img in enumerate(uni):
+        ts.push_tile_with_image(f"{i}.png", colors[i], img)
+    tall = uni.reshape(-1, dim, 3)
+    res = emo.render_nto1(tall, ts, dim, ctx=ctx)
+    assert (res.image == tall).all() and (res.dist == 0).all()
+    for a in range(0, len(uni) - 1, 2):
+        img = np.concatenate([uni[a], uni[a + 1]], 0)
+        res = emo.render_nto1(img, ts, dim, ctx=ctx)
+        assert (res.image == img).all()
+        if a > 40:
+            break
+    # mod.rs:59-68 output dimensions
+    src = np.zeros((2 * dim, 5 * dim, 3), np.uint8)
+    assert emo.render_nto1(src, ts, dim, ctx=ctx).image.shape == (2 * dim, 5 * dim, 3)
+
+
+# ---- compose / tint ------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,ts,T,bh,bw", [(1, 8, 100, 37, 64), (1, 16, 64, 10, 10), (1, 32, 16, 5, 7), (4, 16, 50, 9, 8),
+                                          (1, 8, 20, 3, 5), (1, 4, 20, 6, 8), (1, 5, 9, 4, 3), (9, 12, 30, 5, 6), (1, 64, 4, 2, 3),
+                                          (4, 6, 10, 3, 3), (1, 1, 5, 7, 9)])
+def test_compose_parity(ctx, N, ts, T, bh, bw):
+    rng = np.random.default_rng(ts * 7 + bw)
+    tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    colors = oracle.analyse_tiles(tiles, N)
+    item = rng.integers(1, T + 1, (bh, bw)).astype(np.int32)
+    item[rng.random((bh, bw)) < 0.4] *= -1  # mirrored placements
+    ctx.set_library(colors, tiles)
+    out = ctx.compose(item)
+    assert (out == oracle.render(tiles, item)).all()
+
+
+@pytest.mark.parametrize("A", [0, 1, 64, 85, 127, 128, 153, 170, 200, 254, 255])
+@pytest.mark.parametrize("N,ts", [(1, 8), (1, 32), (4, 16), (1, 6), (4, 8)])
+def test_tint_parity(ctx, A, N, ts):
+    rng = np.random.default_rng(A * 31 + ts)
+    dim = int(N ** 0.5)
+    T, bh, bw = 40, 6, 9
+    tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    # make exceptions likely: tile pixels equal to the source colour
+    src = rng.integers(0, 256, (bh * dim, bw * dim, 3), dtype=np.uint8)
+    tiles[:, ::2, ::2] = src[0, 0]
+    tiles[:, 1::2, ::2, 0] = 255
+    tiles[:, ::2, 1::2, 1] = 0
+    colors = oracle.analyse_tiles(tiles, N)
+    item = rng.integers(1, T + 1, (bh, bw)).astype(np.int32)
+    item[rng.random((bh, bw)) < 0.3] *= -1
+    ctx.set_library(colors, tiles)
+    got = ctx.compose(item, src, 4, A)
+    want = oracle.tint(oracle.render(tiles, item), src, A)
+    assert (got == want).all()
+
+
+def test_tint_all_pairs_every_alpha(ctx):
+    """Every (bg, fg) pair for every alpha through the fast kernel geometry: ts=16 tiles whose
+    16 rows x 16 cols enumerate bg, source pixels enumerate fg."""
+    bg = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    tiles = np.stack([bg, bg[::-1], bg.T], -1)[None]  # [1,16,16,3], each channel a permutation of 0..255
+    src = np.zeros((16, 16, 3), np.uint8)
+    fgv = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    src[..., 0], src[..., 1], src[..., 2] = fgv, fgv[::-1], fgv.T
+    ctx.set_library(np.zeros((1, 1, 3), np.uint8), tiles)
+    item = np.ones((16, 16), np.int32)
+    base = oracle.render(tiles, item)
+    for A in range(256):
+        got = ctx.compose(item, src, 4, A)
+        want = onp.tint(base, src, A)
+        assert (got == want).all(), A
+
+
+def test_compose_errors(ctx):
+    tiles = np.zeros((3, 8, 8, 3), np.uint8)
+    ctx.set_library(np.zeros((3, 1, 3), np.uint8), tiles)
+    for bad in (0, 4, -4):
+        item = np.ones((2, 2), np.int32)
+        item[1, 1] = bad
+        with pytest.raises(emo.EmosaicError, match="item map"):
+            ctx.compose(item)
+    ctx.set_library(np.zeros((3, 1, 3), np.uint8))  # no pixels resident
+    with pytest.raises(emo.EmosaicError, match="no tile pixels"):
+        ctx.compose(np.ones((2, 2), np.int32))
+    with pytest.raises(emo.EmosaicError, match="Tile size must be divisible by 2"):
+        ctx.set_library(np.zeros((3, 4, 3), np.uint8), np.zeros((3, 7, 7, 3), np.uint8))
+
+
+# ---- golden fixtures -----------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_1to1_t300", "c1_1to1_t300_smooth", "c2_4to1_small", "m3_9to1_small",
+                                  "c5_tint_1to1", "tint_4to1_a200"])
+def test_golden(ctx, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    N = int(g["N"])
+    dim = int(N ** 0.5)
+    colors = ctx.analyse_tiles(g["tiles"], dim)
+    assert (colors == g["colors"]).all()
+    ctx.set_library(colors, g["tiles"])
+    item, dist = ctx.match(g["src"])
+    assert (item == g["item"]).all() and (dist == g["dist"]).all()
+    assert sha(ctx.compose(item)) == str(g["out_sha256"])
+    out, it2, d2 = ctx.mosaic(g["src"], 3, 0)
+    assert sha(out) == str(g["out_sha256"]) and (it2 == item).all() and (d2 == dist).all()
+    if "A" in g.files:
+        assert sha(ctx.compose(item, g["src"], 4, int(g["A"]))) == str(g["tint_sha256"])
+        out4, _, _ = ctx.mosaic(g["src"], 4, int(g["A"]))
+        assert sha(out4) == str(g["tint_sha256"])
+
+
+# ---- BASELINE configs at (near) full size: oracle where it finishes in seconds, properties beyond ------
+def test_config2_4to1_full(ctx):
+    """C2: 4to1, 10k tiles, 1024x1024 source, ts 16.  KD-tree oracle (exact, canonical ties) on the full map."""
+    rng = np.random.default_rng(1234)
+    tiles = rng.integers(0, 256, (10000, 16, 16, 3), dtype=np.uint8)
+    src = np.random.default_rng(5678).integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+    colors = ctx.analyse_tiles(tiles, 2)
+    assert (colors == oracle.analyse_tiles(tiles, 4)).all()
+    ctx.set_library(colors, tiles)
+    out, item, dist = ctx.mosaic(src, 3, 0)
+    ri, rd = oracle.KdTree(colors).match(src)
+    assert (dist == rd).all() and (item == ri).all()
+    assert out.shape == (8192, 8192, 3)
+    assert (out == oracle.render(tiles, item)).all()
+
+
+def test_config4_stripe_and_properties(ctx):
+    """C4 geometry (100k tiles, ts 8, 4096-wide source): oracle parity on a 64-row stripe, plus size-independent
+    properties on a 512-row stripe: dist equals the L1 distance to the chosen tile, every placed tile is copied
+    verbatim, and matching the library's own colours returns distance 0 with the smallest duplicate index."""
+    rng = np.random.default_rng(1234)
+    T = 100_000
+    tiles = rng.integers(0, 256, (T, 8, 8, 3), dtype=np.uint8)
+    src = np.random.default_rng(5678).integers(0, 256, (512, 4096, 3), dtype=np.uint8)
+    colors = ctx.analyse_tiles(tiles, 1)
+    ctx.set_library(colors, tiles)
+    out, item, dist = ctx.mosaic(src, 3, 0)
+    kd = oracle.KdTree(colors)
+    ri, rd = kd.match(src[:64])
+    assert (item[:64] == ri).all() and (dist[:64] == rd).all()
+    chosen = colors[np.abs(item) - 1, 0].astype(np.int64)
+    assert (np.abs(chosen - src.astype(np.int64)).sum(-1) == dist).all()
+    assert (item > 0).all()  # 1to1: the mirror coincides and never wins
+    rows = rng.choice(512, 8, replace=False)
+    for r in rows:
+        assert (out[r * 8:(r + 1) * 8] == oracle.render(tiles, item[r:r + 1])).all()
+    # idempotence: the library's own colours as the source
+    self_src = colors[:4096 * 8, 0].reshape(8, 4096, 3)
+    it, ds = ctx.match(self_src)
+    assert (ds == 0).all()
+    ri2, _ = kd.match(self_src)
+    assert (it == ri2).all()
+
+
+def test_config5_tint_large(ctx):
+    """C5 geometry (ts 32, A=127, RGBA out) on a 128x256 source: oracle parity on the whole 4096x8192x4 image."""
+    rng = np.random.default_rng(1234)
+    tiles = rng.integers(0, 256, (4096, 32, 32, 3), dtype=np.uint8)
+    src = np.random.default_rng(5678).integers(0, 256, (128, 256, 3), dtype=np.uint8)
+    colors = ctx.analyse_tiles(tiles, 1)
+    ctx.set_library(colors, tiles)
+    out, item, dist = ctx.mosaic(src, 4, emo.tint_alpha(0.5))
+    ri, rd = oracle.match(colors, src)
+    assert (item == ri).all() and (dist == rd).all()
+    assert (out == oracle.tint(oracle.render(tiles, item), src, 127)).all()
+
+
+def test_mosaic_chunked_pipeline_matches_single_calls(ctx):
+    """emo_mosaic pipelines block-row chunks; result must equal match + compose done in one piece."""
+    rng = np.random.default_rng(2)
+    tiles = rng.integers(0, 256, (2000, 32, 32, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (300, 700, 3), dtype=np.uint8)  # 645 MB RGB out -> several chunks
+    colors = ctx.analyse_tiles(tiles, 1)
+    ctx.set_library(colors, tiles)
+    out, item, dist = ctx.mosaic(src, 3, 0)
+    i2, d2 = ctx.match(src)
+    assert (item == i2).all() and (dist == d2).all()
+    o2 = ctx.compose(i2)
+    assert sha(out) == sha(o2)
