@@ -30,6 +30,8 @@
 
 static constexpr int MATCH_STAGES = 4;
 static constexpr int MATCH_WIN = 16;
+static constexpr int MATCH_UNROLL = 2;
+
 
 // ---------------------------------------------------------------------------------------
 // library build: packed candidates and the (tile, mirrored tile) pixel store
@@ -107,8 +109,8 @@ struct MatchParams {
 };
 
 template <int WORDS, int OFF, int NCW>
-__device__ __forceinline__ uint32_t sad_vec(const uint32_t (&q)[WORDS], const uint32_t (&c)[NCW]) {
-    uint32_t d = 0;
+__device__ __forceinline__ uint32_t sad_vec(const uint32_t (&q)[WORDS], const uint32_t (&c)[NCW], uint32_t acc) {
+    uint32_t d = acc;
 #pragma unroll
     for (int w = 0; w < WORDS; w++) d = sad4(q[w], c[OFF + w], d);
     return d;
@@ -166,7 +168,12 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
     }
 
     // ---- consumers: R queries per thread, packed like the candidates
-    uint32_t q[R][WORDS], best[R], seen[R], idx[R];
+    // best2[r] holds TWO running minima as 16-bit lanes: high lane = candidates at even positions,
+    // low lane = odd positions.  A pair of distances is produced already packed:
+    //   v = sad(q, c_odd, sad(q, c_even, 0) << 16)      (VABSDIFF4.ACC, IMAD.U32 x 0x10000, VABSDIFF4.ACC)
+    // and one VIMNMX3.U16x2 folds four candidates into best2.  ALU pipe: 1.25 instr/pair, FMA pipe: 0.5.
+    // Distances are < 65536 because 255 * 3N <= 12240 for the supported N.
+    uint32_t q[R][WORDS], best2[R], seen2[R], bestd[R], idx[R];
     const uint32_t qbase = blockIdx.x * (uint32_t)(NT * R);
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -187,8 +194,9 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
                     if ((b >> 2) == (uint32_t)w) q[r][w] |= v;
             }
         }
-        best[r] = 0xffffffffu;
-        seen[r] = 0xffffffffu;
+        best2[r] = 0xffffffffu;
+        seen2[r] = 0xffffffffu;
+        bestd[r] = 0xffffffffu;
         idx[r] = 0;
     }
 
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
         const uint32_t cand_base = c * p.chunk;
         for (uint32_t w0 = 0; w0 < p.chunk; w0 += MATCH_WIN) {
             const uint4 *win = reinterpret_cast<const uint4 *>(st + (size_t)w0 * WORDS);
-#pragma unroll 2
+#pragma unroll(MATCH_UNROLL)
             for (int j4 = 0; j4 < MATCH_WIN / 4; j4++) {
                 // 4 candidates = 4*WORDS words = WORDS x LDS.128 (same address in every lane: broadcast)
                 uint32_t cw[4 * WORDS];
@@ -210,29 +218,33 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
                 }
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const uint32_t d0 = sad_vec<WORDS, 0 * WORDS>(q[r], cw);
-                    const uint32_t d1 = sad_vec<WORDS, 1 * WORDS>(q[r], cw);
-                    const uint32_t d2 = sad_vec<WORDS, 2 * WORDS>(q[r], cw);
-                    const uint32_t d3 = sad_vec<WORDS, 3 * WORDS>(q[r], cw);
-                    best[r] = min(best[r], min(d0, d1));  // VIMNMX3
-                    best[r] = min(best[r], min(d2, d3));
+                    const uint32_t e0 = sad_vec<WORDS, 0 * WORDS>(q[r], cw, 0u);
+                    const uint32_t e2 = sad_vec<WORDS, 2 * WORDS>(q[r], cw, 0u);
+                    const uint32_t v01 = sad_vec<WORDS, 1 * WORDS>(q[r], cw, e0 << 16);
+                    const uint32_t v23 = sad_vec<WORDS, 3 * WORDS>(q[r], cw, e2 << 16);
+                    best2[r] = __vimin3_u16x2(best2[r], v01, v23);  // VIMNMX3.U16x2
                 }
             }
-            bool improved = false;
+            bool changed = false;
 #pragma unroll
-            for (int r = 0; r < R; r++) improved |= best[r] < seen[r];
-            if (improved) {
-                // rare: find the FIRST candidate of this window that reaches the new minimum
+            for (int r = 0; r < R; r++) changed |= best2[r] != seen2[r];
+            if (changed) {
+                // rare: a lane minimum dropped inside this window.  If the overall minimum dropped too,
+                // find the FIRST candidate of the window that reaches it (strict `<` keeps earlier ties).
                 const uint32_t *wc = st + (size_t)w0 * WORDS;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    if (best[r] < seen[r]) {
-                        uint32_t found = 0;
+                    if (best2[r] != seen2[r]) {
+                        seen2[r] = best2[r];
+                        const uint32_t m = min(best2[r] >> 16, best2[r] & 0xffffu);
+                        if (m < bestd[r]) {
+                            uint32_t found = 0;
 #pragma unroll
-                        for (int j = MATCH_WIN - 1; j >= 0; j--)
-                            if (sad_vec_rescan<WORDS>(q[r], wc + j * WORDS) == best[r]) found = j;
-                        idx[r] = cand_base + w0 + found;
-                        seen[r] = best[r];
+                            for (int j = MATCH_WIN - 1; j >= 0; j--)
+                                if (sad_vec_rescan<WORDS>(q[r], wc + j * WORDS) == m) found = j;
+                            idx[r] = cand_base + w0 + found;
+                            bestd[r] = m;
+                        }
                     }
                 }
             }
@@ -246,12 +258,12 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
         const uint32_t qi = qbase + r * NT + tid;
         if (qi >= p.Q) continue;
         if (p.keys) {
-            atomicMin(&p.keys[qi], ((unsigned long long)best[r] << 32) | idx[r]);
+            atomicMin(&p.keys[qi], ((unsigned long long)bestd[r] << 32) | idx[r]);
         } else {
             const uint32_t cnd = idx[r];
             const int32_t t1 = (int32_t)(p.mirrored ? (cnd >> 1) : cnd) + 1;
             p.item[qi] = (p.mirrored && (cnd & 1)) ? -t1 : t1;
-            p.dist[qi] = best[r];
+            p.dist[qi] = bestd[r];
         }
     }
 }
@@ -280,7 +292,7 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
     // split the candidate range across CTAs when the query tiles alone cannot fill the GPU
     uint32_t splits = 1;
-    const uint32_t want = (uint32_t)ctx->sm_count * 4;
+    const uint32_t want = (uint32_t)ctx->sm_count * 6;  // >= 3 waves at 2 CTAs/SM
     if (qtiles < want) {
         splits = (want + qtiles - 1) / qtiles;
         if (splits > p.n_chunks) splits = p.n_chunks;
@@ -323,7 +335,7 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
     p.dist = dist;
     p.keys = nullptr;
     const uint32_t Q = p.Q;
-    const bool big = Q >= (uint32_t)ctx->sm_count * 2048u * 2u;
+    const bool big = Q >= 32768u;  // below that the per-CTA query tile shrinks (R=2) to keep the GPU busy
     switch (ctx->words) {
         case 1: return big ? launch_match_t<1, 8, 256>(ctx, p, Q) : launch_match_t<1, 2, 128>(ctx, p, Q);
         case 3: return big ? launch_match_t<3, 8, 256>(ctx, p, Q) : launch_match_t<3, 2, 128>(ctx, p, Q);
