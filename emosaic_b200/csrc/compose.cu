@@ -152,6 +152,63 @@ __global__ void __launch_bounds__(256) compose_copy_kernel(const uint8_t *__rest
     for (; r < ts; r++) VecIO<V>::st(d + (size_t)r * OWB, VecIO<V>::ld(s + (size_t)r * RB));
 }
 
+// Small tiles (ts = 8, 16): a tile row is only 24 / 48 bytes, so the row-wise gather above costs one
+// L1 wavefront per 24..48 bytes and the kernel becomes L1TEX-bound (ncu: l1tex 96 %, dram 60 %).
+// Here a CTA takes G consecutive tiles of one block row (G*3*ts = 1536 B of output per row), reads each
+// tile as ONE contiguous run (192 / 768 B, 16-byte pieces), transposes through shared memory and writes
+// every output row chunk as 1536 contiguous bytes with 16-byte stores.
+template <int TS>
+__global__ void __launch_bounds__(256) compose_tile_kernel(const uint8_t *__restrict__ lib, const int32_t *__restrict__ item,
+                                                           uint32_t T, uint32_t bw, uint8_t *__restrict__ out,
+                                                           int *__restrict__ err) {
+    constexpr int RB = TS * 3;                 // bytes per tile row
+    constexpr int TILE_B = TS * RB;            // bytes per tile
+    constexpr int G = 1536 / RB;               // tiles per CTA
+    constexpr int ROW_CHUNK = G * RB;          // 1536
+    constexpr int STRIDE = ROW_CHUNK + 16;     // padded shared-memory row stride (bank spread)
+    constexpr int PIECES = G * TILE_B / 16;    // 16-byte pieces per CTA (768 / 1536)
+    constexpr int PPT = TILE_B / 16;           // pieces per tile (12 / 48)
+    __shared__ __align__(16) uint8_t sm[TS * STRIDE];
+    __shared__ uint32_t entries[G];
+    const uint32_t by = blockIdx.y, bx0 = blockIdx.x * G;
+    if (threadIdx.x < G) {
+        uint32_t e = 0;
+        if (!item_to_entry(item[(size_t)by * bw + bx0 + threadIdx.x], T, e)) atomicOr(err, 1);
+        entries[threadIdx.x] = e;
+    }
+    __syncthreads();
+    uint4 v[PIECES / 256];
+#pragma unroll
+    for (int k = 0; k < PIECES / 256; k++) {
+        const int p = threadIdx.x + 256 * k;
+        const int tile = p / PPT, part = p % PPT;
+        v[k] = __ldg(reinterpret_cast<const uint4 *>(lib + (size_t)entries[tile] * TILE_B + part * 16));
+    }
+#pragma unroll
+    for (int k = 0; k < PIECES / 256; k++) {
+        const int p = threadIdx.x + 256 * k;
+        const int tile = p / PPT, part = p % PPT;
+        if constexpr (RB % 16 == 0) {
+            const int row = (part * 16) / RB, col = (part * 16) % RB;
+            *reinterpret_cast<uint4 *>(sm + row * STRIDE + tile * RB + col) = v[k];
+        } else {  // RB = 24: the piece straddles rows at 8-byte granularity
+            const int h0 = 2 * part, h1 = 2 * part + 1;
+            *reinterpret_cast<uint2 *>(sm + (h0 / 3) * STRIDE + tile * RB + (h0 % 3) * 8) = make_uint2(v[k].x, v[k].y);
+            *reinterpret_cast<uint2 *>(sm + (h1 / 3) * STRIDE + tile * RB + (h1 % 3) * 8) = make_uint2(v[k].z, v[k].w);
+        }
+    }
+    __syncthreads();
+    const size_t OWB = (size_t)bw * RB;
+    uint8_t *d = out + (size_t)by * TS * OWB + (size_t)bx0 * RB;
+#pragma unroll
+    for (int k = 0; k < PIECES / 256; k++) {
+        const int p = threadIdx.x + 256 * k;
+        const int row = p / (ROW_CHUNK / 16), c16 = p % (ROW_CHUNK / 16);
+        const uint4 o = *reinterpret_cast<const uint4 *>(sm + row * STRIDE + c16 * 16);
+        stg_cs_v4(d + (size_t)row * OWB + c16 * 16, o);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // generic kernel: one thread per output pixel, any geometry, RGB or RGBA(+tint via exact table)
 // ---------------------------------------------------------------------------------------
@@ -267,7 +324,11 @@ int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, ui
     const uint32_t RB = ts * 3;
     const bool aligned = ((uintptr_t)out % 16 == 0) && bh <= 65535;
     if (oc == 3) {
-        if (aligned && RB % 16 == 0) {
+        if (aligned && ts == 8 && bw % 64 == 0) {
+            compose_tile_kernel<8><<<dim3(bw / 64, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
+        } else if (aligned && ts == 16 && bw % 32 == 0) {
+            compose_tile_kernel<16><<<dim3(bw / 32, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
+        } else if (aligned && RB % 16 == 0) {
             const uint32_t pieces = bw * RB / 16;
             compose_copy_kernel<uint4><<<dim3((pieces + 255) / 256, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, ts, bw, out,
                                                                                                 ctx->err_flag);

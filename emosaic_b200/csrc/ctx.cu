@@ -63,6 +63,7 @@ void emo_destroy(emo_ctx *ctx) {
     cudaFree(ctx->cand);
     cudaFree(ctx->lib_px);
     cudaFree(ctx->keys);
+    cudaFree(ctx->qvec);
     cudaFree(ctx->err_flag);
     for (int i = 0; i < 6; i++) cudaFree(ctx->stage[i]);
     cudaFree(ctx->tint.lut);
@@ -294,15 +295,20 @@ static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, boo
     uint32_t dim = 1;
     while (dim * dim < N) dim++;
     uint32_t words = (3 * N + 3) / 4;
-    if (!(words == 1 || words == 3 || words == 7 || words == 12)) {
-        emo_set_error("set_library: N=%u (--mode %u) is not built into this library yet; supported N: 1, 4, 9, 16", N, dim);
+    // --mode 1..4 (N = 1, 4, 9, 16) keep the query vectors in registers; larger N (--mode 5..128, up to
+    // 49 152 bytes per vector) use the tiled wide kernel with vectors padded to a multiple of 32 words.
+    ctx->wide = !(words == 1 || words == 3 || words == 7 || words == 12);
+    if (ctx->wide) words = (words + 31) / 32 * 32;
+    if ((uint64_t)N * 3 * 255 >= (1ull << 32)) {
+        emo_set_error("set_library: N=%u overflows the u32 distance", N);
         return EMO_ERR_UNSUPPORTED;
     }
     ctx->T = T; ctx->N = N; ctx->dim = dim; ctx->ts = ts; ctx->words = words;
     ctx->L = (N == 1) ? T : 2 * T;  // for N == 1 a tile and its mirror coincide; the mirror can never win a tie
-    uint32_t chunk = (words == 1) ? 2048 : (words == 3 ? 1024 : 256);
-    uint32_t l16 = (ctx->L + 15) / 16 * 16;
-    if (l16 < chunk) chunk = l16;
+    uint32_t chunk = (words == 1) ? 1024 : (words == 3 ? 512 : 256);
+    if (ctx->wide) chunk = 64;  // candidate tile of match_wide_kernel
+    uint32_t l32 = (ctx->L + 31) / 32 * 32;  // stages are scanned in windows of 32 candidates (MATCH_WIN)
+    if (l32 < chunk && !ctx->wide) chunk = l32;
     ctx->chunk = chunk;
     ctx->n_chunks = (ctx->L + chunk - 1) / chunk;
     ctx->has_px = has_px;

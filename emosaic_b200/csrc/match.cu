@@ -29,8 +29,8 @@
 #include "common.cuh"
 
 static constexpr int MATCH_STAGES = 4;
-static constexpr int MATCH_WIN = 16;
-static constexpr int MATCH_UNROLL = 2;
+static constexpr int MATCH_WIN = 32;
+static constexpr int MATCH_UNROLL = 4;
 
 
 // ---------------------------------------------------------------------------------------
@@ -182,16 +182,16 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
         const uint32_t by = qi / p.bw, bx = qi % p.bw;
 #pragma unroll
         for (int w = 0; w < WORDS; w++) q[r][w] = 0;
-        // analysis.rs:23-36: cell i of the block is source pixel (x + i % dim, y + i / dim)
-        for (uint32_t i = 0; i < p.dim * p.dim; i++) {
-            const uint8_t *px = p.src + ((size_t)(by * p.dim + i / p.dim) * p.W + (bx * p.dim + i % p.dim)) * 3;
+        // analysis.rs:23-36: cell i of the block is source pixel (x + i % dim, y + i / dim);
+        // byte b of the query vector is channel b % 3 of cell b / 3 (all register indices static)
+        const uint32_t D = 3 * p.dim * p.dim;
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const uint32_t b = i * 3 + ch;
-                const uint32_t v = (uint32_t)px[ch] << (8 * (b & 3));
-#pragma unroll
-                for (int w = 0; w < WORDS; w++)
-                    if ((b >> 2) == (uint32_t)w) q[r][w] |= v;
+        for (int b = 0; b < 4 * WORDS; b++) {
+            if ((uint32_t)b < D) {
+                const uint32_t cell = b / 3, ch = b % 3;
+                const uint32_t cy = cell / p.dim, cx = cell - cy * p.dim;
+                const uint32_t v = p.src[((size_t)(by * p.dim + cy) * p.W + (bx * p.dim + cx)) * 3 + ch];
+                q[r][b >> 2] |= v << (8 * (b & 3));
             }
         }
         best2[r] = 0xffffffffu;
@@ -290,13 +290,22 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8;
     EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
-    // split the candidate range across CTAs when the query tiles alone cannot fill the GPU
+    // Split the candidate range across gridDim.y when the query tiles alone cannot balance the GPU.
+    // The kernel is ALU-bound, so an SM's time is the sum of the work of the CTAs it receives: the model is
+    // total work / #SM + one CTA of tail, with a fixed per-CTA prologue/merge term (in candidate-equivalents).
     uint32_t splits = 1;
-    const uint32_t want = (uint32_t)ctx->sm_count * 6;  // >= 3 waves at 2 CTAs/SM
-    if (qtiles < want) {
-        splits = (want + qtiles - 1) / qtiles;
-        if (splits > p.n_chunks) splits = p.n_chunks;
-        if (splits > 65535) splits = 65535;
+    if (qtiles < (uint32_t)ctx->sm_count * 32u) {
+        const uint32_t max_splits = p.n_chunks < 128 ? p.n_chunks : 128;
+        double best_cost = 1e300;
+        for (uint32_t sp = 1; sp <= max_splits; sp++) {
+            const uint32_t cps = (p.n_chunks + sp - 1) / sp;
+            const uint32_t real = (p.n_chunks + cps - 1) / cps;
+            const double per_cta = (double)cps * p.chunk + 384.0 + (real > 1 ? 64.0 : 0.0);
+            double per_sm = (double)qtiles * real * per_cta / ctx->sm_count;
+            if ((uint64_t)qtiles * real < (uint64_t)ctx->sm_count) per_sm = per_cta;  // fewer CTAs than SMs
+            const double cost = per_sm + per_cta;
+            if (cost < best_cost - 1e-9) { best_cost = cost; splits = real; }
+        }
     }
     p.chunks_per_split = (p.n_chunks + splits - 1) / splits;
     splits = (p.n_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
@@ -319,7 +328,129 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     return EMO_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// wide vectors (N = 25 ... 16384, --mode 5 ... 128): tiled all-pairs kernel
+// ---------------------------------------------------------------------------------------
+// Query vectors do not fit in registers, so this is the classic shared-memory tiling: a CTA owns 64
+// queries, walks candidate tiles of 64, and for every (64 x 64) tile streams the vectors through shared
+// memory in slices of 32 words; each thread accumulates a 4 x 4 block of distances with VABSDIFF4.ACC
+// (2 LDS.128 per 16 VABSDIFF4).  Slices are stored word-major with an XOR swizzle so both the transposing
+// stores and the 128-bit reads are bank-conflict free.  The argmin keeps the canonical order (candidates are
+// visited in increasing rank, strict `<`).
+static constexpr int WQ = 64, WC = 64, WK = 32;
+
+__global__ void pack_queries_kernel(const uint8_t *__restrict__ src, uint32_t W, uint32_t bw, uint32_t Q, uint32_t Qpad,
+                                    uint32_t dim, uint32_t words, uint32_t *__restrict__ qvec) {
+    const uint64_t total = (uint64_t)Qpad * words;
+    const uint32_t D = 3 * dim * dim;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t qi = (uint32_t)(i / words);
+        const uint32_t w = (uint32_t)(i % words);
+        if (qi >= Q) qi = Q - 1;
+        const uint32_t by = qi / bw, bx = qi % bw;
+        uint32_t packed = 0;
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t b = w * 4 + k;
+            if (b < D) {
+                const uint32_t cell = b / 3, ch = b % 3, cy = cell / dim, cx = cell % dim;  // analysis.rs:23-36
+                packed |= (uint32_t)src[((size_t)(by * dim + cy) * W + (bx * dim + cx)) * 3 + ch] << (8 * k);
+            }
+        }
+        qvec[i] = packed;
+    }
+}
+
+__global__ void __launch_bounds__(256) match_wide_kernel(const uint32_t *__restrict__ qvec, const uint32_t *__restrict__ cand,
+                                                         uint32_t words, uint32_t n_ctiles, uint32_t tiles_per_split, uint32_t Q,
+                                                         unsigned long long *__restrict__ keys) {
+    __shared__ __align__(16) uint32_t sq[WK][WQ];
+    __shared__ __align__(16) uint32_t sc[WK][WC];
+    const int tid = threadIdx.x, tq = tid >> 4, tc = tid & 15;
+    const uint32_t q0 = blockIdx.x * WQ;
+    const uint32_t t0 = blockIdx.y * tiles_per_split, t1 = min(t0 + tiles_per_split, n_ctiles);
+    uint32_t bestd[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, besti[4] = {0, 0, 0, 0};
+    // loader mapping: thread -> (row = tid / 8 (+32), quad = tid % 8): 4 consecutive words of one vector
+    const int lrow = tid >> 3, lquad = tid & 7;
+    for (uint32_t t = t0; t < t1; t++) {
+        uint32_t acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0;
+        for (uint32_t k0 = 0; k0 < words; k0 += WK) {
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = lrow + 32 * h;
+                const uint4 vq = __ldg(reinterpret_cast<const uint4 *>(qvec + (size_t)(q0 + row) * words + k0 + lquad * 4));
+                const uint4 vc = __ldg(reinterpret_cast<const uint4 *>(cand + ((size_t)t * WC + row) * words + k0 + lquad * 4));
+                const int col = row ^ (lquad << 2);  // swizzle: word rows 4*lquad..+3 share this column permutation
+                sq[lquad * 4 + 0][col] = vq.x; sq[lquad * 4 + 1][col] = vq.y; sq[lquad * 4 + 2][col] = vq.z; sq[lquad * 4 + 3][col] = vq.w;
+                sc[lquad * 4 + 0][col] = vc.x; sc[lquad * 4 + 1][col] = vc.y; sc[lquad * 4 + 2][col] = vc.z; sc[lquad * 4 + 3][col] = vc.w;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int k = 0; k < WK; k++) {
+                const int sw = (k >> 2) & 7;
+                const uint4 a4 = *reinterpret_cast<const uint4 *>(&sq[k][(tq ^ sw) * 4]);
+                const uint4 c4 = *reinterpret_cast<const uint4 *>(&sc[k][(tc ^ sw) * 4]);
+                const uint32_t qa[4] = {a4.x, a4.y, a4.z, a4.w}, cb[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b] = sad4(qa[a], cb[b], acc[a][b]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (acc[a][b] < bestd[a]) { bestd[a] = acc[a][b]; besti[a] = t * WC + tc * 4 + b; }
+    }
+    // merge the 16 lanes that share a query group (lexicographic (dist, rank) minimum), then across splits
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        unsigned long long key = ((unsigned long long)bestd[a] << 32) | besti[a];
+#pragma unroll
+        for (int m = 1; m < 16; m <<= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
+            key = o < key ? o : key;
+        }
+        const uint32_t qi = q0 + tq * 4 + a;
+        if (tc == 0 && qi < Q) atomicMin(&keys[qi], key);
+    }
+}
+
+static int launch_match_wide(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    const uint32_t dim = ctx->dim, bw = W / dim, Q = bw * (H / dim), words = ctx->words;
+    const uint32_t Qpad = (Q + WQ - 1) / WQ * WQ;
+    int rc = emo_ensure(ctx, (void **)&ctx->qvec, &ctx->qvec_cap, (size_t)Qpad * words * 4);
+    if (rc) return rc;
+    if ((rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, (size_t)Q * 8))) return rc;
+    {
+        const uint64_t total = (uint64_t)Qpad * words, blocks = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 32;
+        pack_queries_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(src, W, bw, Q, Qpad, dim, words, ctx->qvec);
+        EMO_LAUNCH_CHECK(ctx);
+    }
+    match_init_keys_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q);
+    EMO_LAUNCH_CHECK(ctx);
+    const uint32_t qtiles = Qpad / WQ, n_ctiles = ctx->n_chunks;
+    uint32_t splits = 1;
+    const uint32_t want = (uint32_t)ctx->sm_count * 8;
+    if (qtiles < want) splits = (want + qtiles - 1) / qtiles;
+    if (splits > n_ctiles) splits = n_ctiles;
+    if (splits > 65535) splits = 65535;
+    const uint32_t tps = (n_ctiles + splits - 1) / splits;
+    splits = (n_ctiles + tps - 1) / tps;
+    match_wide_kernel<<<dim3(qtiles, splits), 256, 0, ctx->stream>>>(ctx->qvec, ctx->cand, words, n_ctiles, tps, Q, ctx->keys);
+    EMO_LAUNCH_CHECK(ctx);
+    match_finalize_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, 1u, item, dist);
+    EMO_LAUNCH_CHECK(ctx);
+    return EMO_OK;
+}
+
 int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    if (ctx->wide) return launch_match_wide(ctx, src, W, H, item, dist);
     MatchParams p;
     p.cand = ctx->cand;
     p.chunk = ctx->chunk;

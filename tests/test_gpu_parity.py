@@ -98,6 +98,40 @@ def test_match_parity(ctx, N, T, H, W):
     assert (item == ri).all()
 
 
+@pytest.mark.parametrize("N,T,bh,bw", [(25, 300, 9, 11), (36, 150, 7, 5), (64, 500, 12, 9), (256, 200, 5, 6), (1024, 70, 3, 4),
+                                       (4096, 40, 2, 2), (16384, 12, 1, 2), (25, 1, 1, 1), (49, 129, 65, 3)])
+def test_match_wide_modes(ctx, N, T, bh, bw):
+    """--mode 5 ... 128 (main.rs:403-413): vectors of up to 49 152 bytes through match_wide_kernel."""
+    dim = int(N ** 0.5)
+    rng = np.random.default_rng(N + T)
+    colors = rng.integers(0, 256, (T, N, 3), dtype=np.uint8)
+    colors[T // 2] = colors[0]  # duplicate -> tie, smallest idx must win
+    src = rng.integers(0, 256, (bh * dim, bw * dim, 3), dtype=np.uint8)
+    # plant exact and mirrored matches
+    src[:dim, :dim] = colors[T - 1].reshape(dim, dim, 3)
+    if bw > 1:
+        src[:dim, dim:2 * dim] = colors[0].reshape(dim, dim, 3)[:, ::-1]
+    ctx.set_library(colors)
+    item, dist = ctx.match(src)
+    ri, rd = oracle.match(colors, src)
+    assert (dist == rd).all() and (item == ri).all()
+    assert dist[0, 0] == 0
+
+
+def test_wide_mode_end_to_end(ctx):
+    """mode 8 (N = 64), ts 16: analyse -> match -> compose + tint against the oracle."""
+    rng = np.random.default_rng(8)
+    tiles = rng.integers(0, 256, (300, 16, 16, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (5 * 8, 7 * 8, 3), dtype=np.uint8)
+    colors = ctx.analyse_tiles(tiles, 8)
+    assert (colors == oracle.analyse_tiles(tiles, 64)).all()
+    ctx.set_library(colors, tiles)
+    out, item, dist = ctx.mosaic(src, 4, 100)
+    ri, rd = oracle.match(colors, src)
+    assert (item == ri).all() and (dist == rd).all()
+    assert (out == oracle.tint(oracle.render(tiles, ri), src, 100)).all()
+
+
 def test_match_ties_and_duplicates(ctx):
     # heavy exact ties: 8-colour palette, many duplicate tiles; the canonical winner is the smallest idx
     g = np.load(os.path.join(GOLD, "ties_palette.npz"))
@@ -135,8 +169,6 @@ def test_match_errors(ctx):
         ctx.match(np.zeros((5, 4, 3), np.uint8))
     with pytest.raises(emo.EmosaicError, match="not a square"):
         ctx.set_library(np.zeros((3, 5, 3), np.uint8))
-    with pytest.raises(emo.EmosaicError):  # N=25 (--mode 5) not built yet: loud, not silent
-        ctx.set_library(np.zeros((3, 25, 3), np.uint8))
     c2 = emo.Context(0)
     with pytest.raises(emo.EmosaicError, match="no library"):
         c2.match(np.zeros((4, 4, 3), np.uint8))
@@ -170,7 +202,7 @@ def test_universe_roundtrip(ctx, N):
 # ---- compose / tint ------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,ts,T,bh,bw", [(1, 8, 100, 37, 64), (1, 16, 64, 10, 10), (1, 32, 16, 5, 7), (4, 16, 50, 9, 8),
                                           (1, 8, 20, 3, 5), (1, 4, 20, 6, 8), (1, 5, 9, 4, 3), (9, 12, 30, 5, 6), (1, 64, 4, 2, 3),
-                                          (4, 6, 10, 3, 3), (1, 1, 5, 7, 9)])
+                                          (4, 6, 10, 3, 3), (1, 1, 5, 7, 9), (1, 16, 64, 5, 64), (4, 16, 40, 4, 32), (1, 8, 50, 3, 128), (1, 8, 50, 2, 192)])
 def test_compose_parity(ctx, N, ts, T, bh, bw):
     rng = np.random.default_rng(ts * 7 + bw)
     tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
