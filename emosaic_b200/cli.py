@@ -1,0 +1,177 @@
+"""Command line with the reference's surface for the accelerated path.
+
+    python -m emosaic_b200 [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [--mode 1|2|...|128|random] [-f] [-t X]
+                           [--downsample K] [--extensions jpg jpeg]
+    python -m emosaic_b200 ... IMG mosaic TILES_DIR -m 1to1|4to1|random        (README spelling)
+
+Mirrors src/main.rs:28-138 (flags), :542-667 (n_to_1: dimension rule, cache, render) and :447-478 (tint).
+Decoding, resizing and directory walking stay on the host (PIL) and outside the accelerated path; tile
+preparation here is decode -> EXIF transpose -> optional centre-square crop -> Lanczos resize (the reference's
+white-border trimming and its ~/.cache/mosaic JPEG cache are host stages that are not reproduced).
+--no-repeat / --randomize / --greedy / --html / --web are rejected: outside the accelerated path.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from typing import List, Optional
+
+import numpy as np
+
+from . import api, cache, stats
+
+MODES = {"1": 1, "2": 2, "3": 3, "4": 4, "5": 5, "6": 6, "8": 8, "16": 16, "32": 32, "64": 64, "128": 128,
+         "1to1": 1, "4to1": 2, "random": "random"}
+
+
+def find_images(root: str, extensions) -> List[str]:
+    """src/mosaic/image.rs:7-23: iterative DFS, extension predicate."""
+    out, stack = [], [root]
+    while stack:
+        d = stack.pop()
+        for e in sorted(os.scandir(d), key=lambda e: e.name):
+            if e.is_dir(follow_symlinks=True):
+                stack.append(e.path)
+            elif os.path.splitext(e.name)[1][1:] in extensions:
+                out.append(e.path)
+    return out
+
+
+def prepare_tile(path: str, tile_size: int, crop: bool) -> np.ndarray:
+    from PIL import Image, ImageOps
+    im = ImageOps.exif_transpose(Image.open(path)).convert("RGB")
+    if crop:
+        w, h = im.size
+        s = min(w, h)
+        im = im.crop(((w - s) // 2, (h - s) // 2, (w - s) // 2 + s, (h - s) // 2 + s))
+    return np.asarray(im.resize((tile_size, tile_size), Image.LANCZOS), dtype=np.uint8)
+
+
+def exif_date(path: str) -> Optional[str]:
+    try:
+        from PIL import Image
+        ex = Image.open(path).getexif()
+        v = ex.get(36867) or ex.get_ifd(0x8769).get(36867) or ex.get(306)
+        return str(v)[:10] if v else None
+    except Exception:
+        return None
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(prog="emosaic", description="Mosaic generator (B200 path)")
+    p.add_argument("-s", "--tile-size", type=int, default=16)
+    p.add_argument("-o", "--output-path", default="./output.jpg")
+    p.add_argument("--crop", action="store_true")
+    p.add_argument("--device", type=int, default=0)
+    p.add_argument("img")
+    sub = p.add_subparsers(dest="subcmd")
+    sub.add_parser("prepare")
+    m = sub.add_parser("mosaic")
+    m.add_argument("tiles_dir")
+    m.add_argument("-m", "--mode", default="1", choices=sorted(MODES))
+    m.add_argument("-f", "--force", action="store_true")
+    m.add_argument("-t", "--tint-opacity", type=float, default=0.0)
+    m.add_argument("--no-repeat", action="store_true")
+    m.add_argument("--downsample", type=int, default=1)
+    m.add_argument("--randomize", type=float, default=None)
+    m.add_argument("--extensions", nargs="+", default=["jpg", "jpeg"])
+    m.add_argument("--greedy", action="store_true")
+    m.add_argument("--html", action="store_true")
+    m.add_argument("--web", action="store_true")
+    m.add_argument("--title", default="Mosaic Widget")
+    m.add_argument("--seed", type=int, default=None, help="random mode only: host RNG seed (the reference uses thread_rng)")
+    return p
+
+
+def main(argv=None) -> int:
+    args = build_parser().parse_args(argv)
+    from PIL import Image
+    ts = args.tile_size
+    if args.subcmd == "prepare":
+        Image.fromarray(prepare_tile(args.img, ts, args.crop)).save(args.output_path)
+        return 0
+    if args.subcmd != "mosaic":
+        print("error: a subcommand is required (mosaic | prepare)", file=sys.stderr)
+        return 2
+    if not (0.0 <= args.tint_opacity <= 1.0):
+        print("error: Value must be between 0 and 1", file=sys.stderr)
+        return 2
+    if args.no_repeat or args.randomize is not None or args.greedy or args.html or args.web:
+        print("error: --no-repeat/--randomize/--greedy/--html/--web are outside the accelerated path", file=sys.stderr)
+        return 2
+    if not os.path.isdir(args.tiles_dir):
+        print(f"error: tiles directory {args.tiles_dir} does not exist", file=sys.stderr)
+        return 1
+    mode = MODES[args.mode]
+    print(f"Opening source image: {args.img}", file=sys.stderr)
+    original = np.asarray(Image.open(args.img).convert("RGB"), dtype=np.uint8)
+    ctx = api.Context(args.device)
+    exts = set(args.extensions)
+
+    if mode == "random":  # main.rs:414-442 + rendering.rs:418-440: uniform random tile per source pixel
+        paths = [p for p in find_images(args.tiles_dir, exts) if os.path.exists(p)]
+        print(f"Tile set with {len(paths)} tiles", file=sys.stderr)
+        px = np.stack([prepare_tile(p, ts, True) for p in paths])
+        ctx.set_library(np.zeros((len(paths), 1, 3), np.uint8), px)
+        item = np.random.default_rng(args.seed).integers(1, len(paths) + 1, original.shape[:2]).astype(np.int32)
+        out = ctx.compose(item)
+        src_for_tint, dist, dim = original, None, 1
+    else:
+        dim = int(mode)
+        N = dim * dim
+        nw, nh = api.adjust_source_dims(original.shape[1], original.shape[0], args.downsample, dim)  # main.rs:567-587
+        print(f"Resizing source image from {original.shape[1]}x{original.shape[0]} to {nw}x{nh}", file=sys.stderr)
+        img = original if (nw, nh) == (original.shape[1], original.shape[0]) else np.asarray(
+            Image.fromarray(original).resize((nw, nh), Image.LANCZOS), dtype=np.uint8)
+        if img.shape[1] % dim or img.shape[0] % dim:
+            print(f"Invalid source dimensions ({img.shape[1]}x{img.shape[0]}): Dimensions must be divisible by {dim}", file=sys.stderr)
+            return 1
+        if ts % dim:
+            print(f"Invalid tile size: Tile size must be divisible by {dim}", file=sys.stderr)
+            return 1
+        cache_path = os.path.join(args.tiles_dir, cache.cache_file_name(N, args.crop))
+        colors = paths = dates = px_render = None
+        if not args.force and os.path.exists(cache_path):  # main.rs:617-654
+            try:
+                colors, paths, dates = cache.deserialize_tile_set(open(cache_path, "rb").read(), N, exts, check_exists=True)
+                print("Reusing analysis cache", file=sys.stderr)
+            except ValueError:
+                colors = None
+        if colors is None:  # generate_tile_set, main.rs:740-813, analysis on the GPU in one batch
+            paths = find_images(args.tiles_dir, exts)
+            px = np.stack([prepare_tile(p, ts, args.crop) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
+            dates = [exif_date(p) for p in paths]
+            colors = ctx.analyse_tiles(px, dim)
+            with open(cache_path, "wb") as f:
+                f.write(cache.serialize_tile_set(colors, paths, dates))
+            if args.crop:
+                px_render = px
+        # tileset.rs:152-155: a TileSet built by from_tiles holds no images, so rendering always (re)prepares
+        # the tiles with crop = true, whatever --crop was used for the analysis
+        if px_render is None:
+            px_render = np.stack([prepare_tile(p, ts, True) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
+        px = px_render
+        print(f"Tile set with {len(paths)} tiles", file=sys.stderr)
+        if len(paths) == 0:
+            print("error: no tiles", file=sys.stderr)
+            return 1
+        ctx.set_library(colors, px)
+        out, item, dist = ctx.mosaic(img, 3, 0)
+        stats.summarise(item, dist, paths)
+        src_for_tint = img
+
+    if args.tint_opacity > 0.0:  # main.rs:447-478: RGBA PNG, early return (no stats image)
+        rgba = ctx.compose(item, src_for_tint, 4, api.tint_alpha(args.tint_opacity))
+        Image.fromarray(rgba, "RGBA").save(args.output_path, format="PNG")
+        return 0
+    print(f"Writing output file to {args.output_path}", file=sys.stderr)
+    Image.fromarray(out).save(args.output_path, format="PNG")  # main.rs:483 save_with_format(Png)
+    if dist is not None:
+        sp = os.path.splitext(args.output_path)[0] + ".stats.png"
+        Image.fromarray(stats.render(dist, dim, ts)).save(sp, format="PNG")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

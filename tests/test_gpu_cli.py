@@ -1,0 +1,94 @@
+"""The reference-shaped command line end to end on the GPU: cache build (-f), cache reuse, 1to1 / 4to1 / random,
+tint.  Decoded tiles are re-prepared on the host and the expected images come from the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from emosaic_b200 import cache, cli
+
+pytestmark = pytest.mark.gpu
+PIL = pytest.importorskip("PIL.Image")
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    tiles = d / "tiles"
+    (tiles / "sub").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    for i in range(60):
+        base = rng.integers(0, 256, 3)
+        img = np.clip(base + rng.integers(-30, 31, (40, 52, 3)), 0, 255).astype(np.uint8)
+        img[:, :20] = np.clip(img[:, :20].astype(int) - 60, 0, 255)  # left/right asymmetry -> mirrored matches in 4to1
+        p = tiles / ("sub" if i % 3 == 0 else "") / f"t{i:03d}.{'jpg' if i % 2 else 'jpeg'}"
+        PIL.fromarray(img).save(p, quality=95)
+    (tiles / "notes.txt").write_text("not an image")
+    PIL.fromarray(rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)).save(tiles / "ignored.png")
+    src = rng.integers(0, 256, (36, 48, 3), dtype=np.uint8)
+    PIL.fromarray(src).save(d / "src.png")
+    return d, src
+
+
+def expected(tiles_dir, src, dim, ts, crop):
+    paths = cli.find_images(str(tiles_dir), {"jpg", "jpeg"})
+    px_an = np.stack([cli.prepare_tile(p, ts, crop) for p in paths])
+    px_rd = np.stack([cli.prepare_tile(p, ts, True) for p in paths])
+    colors = oracle.analyse_tiles(px_an, dim * dim)
+    item, dist = oracle.match(colors, src)
+    return paths, colors, item, dist, px_an, px_rd
+
+
+@pytest.mark.parametrize("mode,dim", [("1", 1), ("4to1", 2), ("3", 3)])
+def test_cli_mosaic_and_cache(workdir, mode, dim):
+    d, src = workdir
+    ts = 12
+    out = d / f"out_{mode}.png"
+    cpath = d / "tiles" / cache.cache_file_name(dim * dim, False)
+    if cpath.exists():
+        cpath.unlink()
+    argv = ["-s", str(ts), "-o", str(out), str(d / "src.png"), "mosaic", str(d / "tiles"), "-m", mode]
+    assert cli.main(argv + ["-f"]) == 0
+    paths, colors, item, dist, px_an, px_rd = expected(d / "tiles", src, dim, ts, False)
+    # analysis uses the un-cropped tiles, rendering always re-prepares with crop = true (tileset.rs:152-155)
+    assert (np.asarray(PIL.open(out)) == oracle.render(px_rd, item)).all()
+    # cache bytes are the reference's bincode layout
+    assert cpath.read_bytes() == oracle.cache_serialize(colors, np.arange(1, len(paths) + 1), [None] * len(paths), paths)
+    assert os.path.exists(str(out)[:-4] + ".stats.png")
+    # second run reuses the cache (tiles re-prepared with crop = true, tileset.rs:152-155)
+    assert cli.main(argv) == 0
+    assert (np.asarray(PIL.open(out)) == oracle.render(px_rd, item)).all()
+    # a vanished tile is filtered and the rest renumbered (main.rs:624-654)
+    victim = paths[5]
+    os.rename(victim, victim + ".bak")
+    try:
+        assert cli.main(argv) == 0
+        keep = [i for i in range(len(paths)) if i != 5]
+        it2, _ = oracle.match(colors[keep], src)
+        assert (np.asarray(PIL.open(out)) == oracle.render(px_rd[keep], it2)).all()
+    finally:
+        os.rename(victim + ".bak", victim)
+
+
+def test_cli_tint_and_random(workdir):
+    d, src = workdir
+    ts = 8
+    out = d / "tint.png"
+    assert cli.main(["-s", str(ts), "-o", str(out), "--crop", str(d / "src.png"), "mosaic", str(d / "tiles"), "-t", "0.5", "-f"]) == 0
+    paths, colors, item, dist, px_an, px_rd = expected(d / "tiles", src, 1, ts, True)
+    got = np.asarray(PIL.open(out))
+    assert got.shape == (36 * ts, 48 * ts, 4)
+    assert (got == oracle.tint(oracle.render(px_an, item), src, 127)).all()
+    assert (d / "tiles" / ".emosaic_1to1_cropped").exists()
+    out2 = d / "rand.png"
+    assert cli.main(["-s", str(ts), "-o", str(out2), str(d / "src.png"), "mosaic", str(d / "tiles"), "-m", "random", "--seed", "3"]) == 0
+    assert np.asarray(PIL.open(out2)).shape == (36 * ts, 48 * ts, 3)  # mod.rs:48-57
+
+
+def test_cli_rejects(workdir):
+    d, _ = workdir
+    base = ["-s", "8", str(d / "src.png"), "mosaic", str(d / "tiles")]
+    assert cli.main(base + ["--no-repeat"]) == 2
+    assert cli.main(["-s", "9", str(d / "src.png"), "mosaic", str(d / "tiles"), "-m", "2"]) == 1  # tile size % dim
+    assert cli.main(["-s", "8", str(d / "src.png"), "mosaic", str(d / "nope")]) == 1

@@ -123,3 +123,31 @@ def test_render_nto1_rejects_like_reference():
         emo.render_nto1(np.zeros((4, 4, 3), np.uint8), ts, 7)
     with pytest.raises(emo.EmosaicError):
         emo.render_nto1(np.zeros((4, 4, 3), np.uint8), ts, 8, no_repeat=True)
+
+
+def test_stats_summary_and_image():
+    # stats.rs:87-195 from the (item, dist) maps
+    import io
+    from emosaic_b200 import stats
+    item = np.array([[1, -2, 1], [3, 1, 2]])
+    dist = np.array([[5, 9, 0], [7, 7, 1]], dtype=np.uint32)
+    buf = io.StringIO()
+    s = stats.summarise(item, dist, ["a", "b", "c"], file=buf)
+    assert s["total"] == 6 and s["unique"] == 3 and abs(s["average_distance"] - 29 / 6) < 1e-12
+    assert s["top"][0] == ("a", 3) and s["worst"][0] == ("b", 9)
+    assert "Average color distance: 4.833" in buf.getvalue()
+    img = stats.render(dist, 1, 1)
+    assert img[:, :, 0].tolist() == [[141, 255, 0], [198, 198, 28]]  # (d / max_d * 255) as u8
+    assert stats.render(np.zeros((2, 2), np.uint32), 1, 1).max() == 0
+    assert stats.render(dist, 2, 4).shape == (1, 2, 3)  # source coordinates / tile_size, stats.rs:176-178
+    with pytest.raises(ValueError):
+        stats.render(np.zeros((0, 0), np.uint32), 1, 1)
+
+
+def test_cli_parser_accepts_both_spellings():
+    from emosaic_b200 import cli
+    p = cli.build_parser()
+    a = p.parse_args(["-s", "8", "img.png", "mosaic", "tiles", "-m", "4to1", "-t", "0.5", "-f"])
+    assert cli.MODES[a.mode] == 2 and a.force and a.tint_opacity == 0.5 and a.tile_size == 8
+    a = p.parse_args(["img.png", "mosaic", "tiles", "--mode", "128"])
+    assert cli.MODES[a.mode] == 128 and a.tile_size == 16 and a.output_path == "./output.jpg"
