@@ -165,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "composed_output_gbs": tot_out / tot / 1e9,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -341,7 +341,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
 
 
@@ -424,7 +424,20 @@ def extras(ctx, torch, dev, hbm_peak, peak_src):
     return ex
 
 
+def emit(line: dict):
+    """Exactly one JSON line on the real stdout (library banners such as NCCL's go to stderr, see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # NCCL / torchrun print banners on stdout; keep stdout for the single JSON line the driver parses
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

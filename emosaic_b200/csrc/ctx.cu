@@ -307,8 +307,8 @@ static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, boo
     ctx->L = (N == 1) ? T : 2 * T;  // for N == 1 a tile and its mirror coincide; the mirror can never win a tie
     uint32_t chunk = (words == 1) ? 1024 : (words == 3 ? 512 : 256);
     if (ctx->wide) chunk = 64;  // candidate tile of match_wide_kernel
-    uint32_t l32 = (ctx->L + 31) / 32 * 32;  // stages are scanned in windows of 32 candidates (MATCH_WIN)
-    if (l32 < chunk && !ctx->wide) chunk = l32;
+    uint32_t lwin = (ctx->L + 127) / 128 * 128;  // stages are scanned in windows of 128 candidates (MATCH_WIN)
+    if (lwin < chunk && !ctx->wide) chunk = lwin;
     ctx->chunk = chunk;
     ctx->n_chunks = (ctx->L + chunk - 1) / chunk;
     ctx->has_px = has_px;

@@ -26,10 +26,12 @@
 // candidates the thread checks whether any of its minima dropped and only then rescans that
 // window for the first candidate that reaches the new minimum (an improvement happens O(log L)
 // times per query, so the rescan is rare and the common path is 1.5 instructions per pair).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static constexpr int MATCH_STAGES = 4;
-static constexpr int MATCH_WIN = 32;
+static constexpr int MATCH_WIN = 128;  // candidates between two argmin checks
 static constexpr int MATCH_UNROLL = 4;
 
 
@@ -116,22 +118,8 @@ __device__ __forceinline__ uint32_t sad_vec(const uint32_t (&q)[WORDS], const ui
     return d;
 }
 
-// Same distance for the rare rescan path. `volatile` keeps the compiler from merging the rescan
-// with the main loop (which would put a compare+select on every pair).
-template <int WORDS>
-__device__ __forceinline__ uint32_t sad_vec_rescan(const uint32_t (&q)[WORDS], const uint32_t *c) {
-    uint32_t d = 0;
-#pragma unroll
-    for (int w = 0; w < WORDS; w++) {
-        uint32_t t;
-        asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(t) : "r"(q[w]), "r"(c[w]), "r"(d));
-        d = t;
-    }
-    return d;
-}
-
 template <int WORDS, int R, int NT>
-__global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const MatchParams p) {
+__global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : (WORDS > 4 ? 3 : 6))) match_kernel(const MatchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage_words = p.chunk * WORDS;
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem);
@@ -225,32 +213,63 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : 3)) match_kernel(const 
                     best2[r] = __vimin3_u16x2(best2[r], v01, v23);  // VIMNMX3.U16x2
                 }
             }
+            // Lazy argmin: remember only WHICH window last lowered the overall minimum (no rescan here).
             bool changed = false;
 #pragma unroll
             for (int r = 0; r < R; r++) changed |= best2[r] != seen2[r];
             if (changed) {
-                // rare: a lane minimum dropped inside this window.  If the overall minimum dropped too,
-                // find the FIRST candidate of the window that reaches it (strict `<` keeps earlier ties).
-                const uint32_t *wc = st + (size_t)w0 * WORDS;
+                const uint32_t wpos = cand_base + w0;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    if (best2[r] != seen2[r]) {
-                        seen2[r] = best2[r];
-                        const uint32_t m = min(best2[r] >> 16, best2[r] & 0xffffu);
-                        if (m < bestd[r]) {
-                            uint32_t found = 0;
-#pragma unroll
-                            for (int j = MATCH_WIN - 1; j >= 0; j--)
-                                if (sad_vec_rescan<WORDS>(q[r], wc + j * WORDS) == m) found = j;
-                            idx[r] = cand_base + w0 + found;
-                            bestd[r] = m;
-                        }
-                    }
+                    const uint32_t m = min(best2[r] >> 16, best2[r] & 0xffffu);
+                    seen2[r] = best2[r];
+                    if (m < bestd[r]) { bestd[r] = m; idx[r] = wpos; }  // strict `<`: an equal later window never wins
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // Epilogue: the winner is the FIRST candidate of the remembered window that reaches the minimum
+    // (candidates are scanned in rank order, so this is the canonical smallest-rank tie-break).
+    // The window is re-read from global memory (L2-resident) with batched 128-bit loads.
+#pragma unroll 1
+    for (int r = 0; r < R; r++) {
+        // runtime-indexed copy of this query (R is small; the selects are cheap and happen once per query)
+        uint32_t qr[WORDS], br = 0, ir = 0;
+#pragma unroll
+        for (int rr = 0; rr < R; rr++)
+            if (rr == r) {
+#pragma unroll
+                for (int w = 0; w < WORDS; w++) qr[w] = q[rr][w];
+                br = bestd[rr];
+                ir = idx[rr];
+            }
+        const uint4 *wc = reinterpret_cast<const uint4 *>(p.cand + (size_t)ir * WORDS);
+        uint32_t found = MATCH_WIN - 1;
+        constexpr int GB = WORDS <= 2 ? 4 : (WORDS <= 4 ? 2 : 1);  // groups of 4 candidates loaded per batch
+        for (int g0 = MATCH_WIN / 4 - GB; g0 >= 0; g0 -= GB) {
+            uint4 buf[GB * WORDS];
+#pragma unroll
+            for (int i = 0; i < GB * WORDS; i++) buf[i] = __ldg(wc + g0 * WORDS + i);
+#pragma unroll
+            for (int g = GB - 1; g >= 0; g--) {
+                uint32_t cw[4 * WORDS];
+#pragma unroll
+                for (int v = 0; v < WORDS; v++) {
+                    cw[4 * v + 0] = buf[g * WORDS + v].x; cw[4 * v + 1] = buf[g * WORDS + v].y;
+                    cw[4 * v + 2] = buf[g * WORDS + v].z; cw[4 * v + 3] = buf[g * WORDS + v].w;
+                }
+                if (sad_vec<WORDS, 3 * WORDS>(qr, cw, 0u) == br) found = (g0 + g) * 4 + 3;
+                if (sad_vec<WORDS, 2 * WORDS>(qr, cw, 0u) == br) found = (g0 + g) * 4 + 2;
+                if (sad_vec<WORDS, 1 * WORDS>(qr, cw, 0u) == br) found = (g0 + g) * 4 + 1;
+                if (sad_vec<WORDS, 0 * WORDS>(qr, cw, 0u) == br) found = (g0 + g) * 4 + 0;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; rr++)
+            if (rr == r) idx[rr] = ir + found;
     }
 
 #pragma unroll
@@ -290,22 +309,24 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8;
     EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
-    // Split the candidate range across gridDim.y when the query tiles alone cannot balance the GPU.
-    // The kernel is ALU-bound, so an SM's time is the sum of the work of the CTAs it receives: the model is
-    // total work / #SM + one CTA of tail, with a fixed per-CTA prologue/merge term (in candidate-equivalents).
+    // Split the candidate range across gridDim.y only when the query tiles cannot fill ~3 waves of resident
+    // CTAs, and never below ~16k candidates per CTA: every CTA pays a fixed prologue (query gather, pipeline
+    // fill) and epilogue (window rescan, merge), measured with tools/sweep_match.py.
+    int occ = 1;
+    EMO_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT + 32, smem));
+    if (occ < 1) occ = 1;
+    const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)occ;
     uint32_t splits = 1;
-    if (qtiles < (uint32_t)ctx->sm_count * 32u) {
-        const uint32_t max_splits = p.n_chunks < 128 ? p.n_chunks : 128;
-        double best_cost = 1e300;
-        for (uint32_t sp = 1; sp <= max_splits; sp++) {
-            const uint32_t cps = (p.n_chunks + sp - 1) / sp;
-            const uint32_t real = (p.n_chunks + cps - 1) / cps;
-            const double per_cta = (double)cps * p.chunk + 384.0 + (real > 1 ? 64.0 : 0.0);
-            double per_sm = (double)qtiles * real * per_cta / ctx->sm_count;
-            if ((uint64_t)qtiles * real < (uint64_t)ctx->sm_count) per_sm = per_cta;  // fewer CTAs than SMs
-            const double cost = per_sm + per_cta;
-            if (cost < best_cost - 1e-9) { best_cost = cost; splits = real; }
-        }
+    if (qtiles < 3 * slots) {
+        const uint32_t by_fill = (3 * slots + qtiles - 1) / qtiles;
+        const uint32_t by_len = (p.n_chunks * p.chunk) / 16384u;
+        splits = by_fill < by_len ? by_fill : by_len;
+        if (splits < 1) splits = 1;
+        if (splits > p.n_chunks) splits = p.n_chunks;
+    }
+    if (const char *e = getenv("EMO_MATCH_SPLITS")) {  // tuning override
+        const int v = atoi(e);
+        if (v >= 1) splits = (uint32_t)v < p.n_chunks ? (uint32_t)v : p.n_chunks;
     }
     p.chunks_per_split = (p.n_chunks + splits - 1) / splits;
     splits = (p.n_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
@@ -466,7 +487,10 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
     p.dist = dist;
     p.keys = nullptr;
     const uint32_t Q = p.Q;
-    const bool big = Q >= 32768u;  // below that the per-CTA query tile shrinks (R=2) to keep the GPU busy
+    // R = 8 queries per thread amortises the candidate loads best but needs long scans and many queries to pay
+    // for its 2048-query CTAs; otherwise 256-query CTAs (R = 2) balance better (tools/sweep_match.py).
+    bool big = Q >= 65536u && ctx->L >= 32768u && ctx->words == 1;
+    if (const char *e = getenv("EMO_MATCH_R")) big = atoi(e) >= 8;  // tuning override
     switch (ctx->words) {
         case 1: return big ? launch_match_t<1, 8, 256>(ctx, p, Q) : launch_match_t<1, 2, 128>(ctx, p, Q);
         case 3: return big ? launch_match_t<3, 8, 256>(ctx, p, Q) : launch_match_t<3, 2, 128>(ctx, p, Q);
