@@ -46,7 +46,8 @@ struct emo_tint_tables {
     uint8_t *lut = nullptr;   // [256 bg][256 fg] exact f32 blend results          (device)
     uint8_t *excv = nullptr;  // [4][256 fg] exceptional bg values                   (device)
     uint8_t *excm = nullptr;  // [4][256 fg] 0x80 where excv is valid                (device)
-    uint32_t *meta = nullptr; // [0] = max exceptions per fg, [1] = alpha byte, [2] = sanity errors (device)
+    uint8_t *cadd = nullptr;  // [256 fg] additive constant 0/1 of the lane formula      (device)
+    uint32_t *meta = nullptr; // [0] = max exceptions per fg, [1] = alpha byte, [2] = sanity errors, [3] = non-uniform fg (device)
 };
 
 struct emo_ctx {
@@ -136,6 +137,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// TMA 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;

@@ -40,11 +40,11 @@ __device__ __forceinline__ uint8_t blend_exact(uint32_t bg, uint32_t fg, uint32_
 
 // grid 256 (fg), block 256 (bg)
 __global__ void tint_tables_kernel(uint32_t A, uint8_t *__restrict__ lut, uint8_t *__restrict__ excv,
-                                   uint8_t *__restrict__ excm, uint32_t *__restrict__ meta) {
-    __shared__ uint32_t n_exc;
+                                   uint8_t *__restrict__ excm, uint8_t *__restrict__ cadd, uint32_t *__restrict__ meta) {
+    __shared__ uint32_t n_exc, n_r0;
     __shared__ uint8_t list[256];
     const uint32_t fg = blockIdx.x, bg = threadIdx.x;
-    if (bg == 0) n_exc = 0;
+    if (bg == 0) { n_exc = 0; n_r0 = 0; }
     __syncthreads();
     uint8_t ab = 255, v;
     if (A == 0) v = (uint8_t)bg;            // fg.a == 0: keep bg
@@ -53,6 +53,7 @@ __global__ void tint_tables_kernel(uint32_t A, uint8_t *__restrict__ lut, uint8_
     lut[bg * 256 + fg] = v;
     const uint32_t x = fg * A + bg * (255 - A);
     const uint32_t q = x / 255, rem = x % 255;
+    if (rem == 0 && x > 0) atomicAdd(&n_r0, 1);
     if (v != q) {
         // the fast path relies on: exception => exact quotient integral, result q-1, bg > 0
         if (!(rem == 0 && v + 1 == q && bg > 0)) atomicAdd(&meta[2], 1);
@@ -62,6 +63,12 @@ __global__ void tint_tables_kernel(uint32_t A, uint8_t *__restrict__ lut, uint8_
     if (bg == 0) {
         atomicMax(&meta[0], n_exc);
         if (fg == 0) meta[1] = ab;
+        // "uniform" fg: either no exception, or EVERY bg whose exact quotient is integral (x > 0) is an
+        // exception.  Then q = (Y + (Y >> 8)) >> 8 with Y = x + 1 (no exception) or Y = x (all exceptions:
+        // that form yields q-1 exactly at the integral quotients) needs no per-pixel fix-up at all.
+        const bool uniform = n_exc == 0 || n_exc == n_r0;
+        if (!uniform) atomicAdd(&meta[3], 1);
+        cadd[fg] = (n_exc != 0 && uniform) ? 0 : 1;
         // deterministic order
         for (uint32_t i = 1; i < n_exc; i++)
             for (uint32_t j = i; j > 0 && list[j - 1] > list[j]; j--) {
@@ -81,15 +88,21 @@ int emo_prepare_tint(emo_ctx *ctx, uint8_t alpha) {
         EMO_CK(cudaMalloc(&t.lut, 65536));
         EMO_CK(cudaMalloc(&t.excv, 1024));
         EMO_CK(cudaMalloc(&t.excm, 1024));
+        EMO_CK(cudaMalloc(&t.cadd, 256));
         EMO_CK(cudaMalloc(&t.meta, 16));
     }
     EMO_CK(cudaMemsetAsync(t.meta, 0, 16, ctx->stream));
-    tint_tables_kernel<<<256, 256, 0, ctx->stream>>>(alpha, t.lut, t.excv, t.excm, t.meta);
+    tint_tables_kernel<<<256, 256, 0, ctx->stream>>>(alpha, t.lut, t.excv, t.excm, t.cadd, t.meta);
     EMO_LAUNCH_CHECK(ctx);
     uint32_t meta[4];
     EMO_CK(cudaMemcpyAsync(meta, t.meta, 16, cudaMemcpyDeviceToHost, ctx->stream));
     EMO_CK(cudaStreamSynchronize(ctx->stream));
     t.K = (meta[2] != 0 || alpha == 0 || alpha == 255) ? 99 : (int)meta[0];  // 99: fast path not applicable
+    if (t.K != 99 && meta[3] == 0) {
+        t.K = 0;  // every fg is uniform: the per-fg additive constant carries the exceptions
+    } else {
+        EMO_CK(cudaMemsetAsync(t.cadd, 1, 256, ctx->stream));
+    }
     t.alpha_out = (uint8_t)meta[1];
     t.alpha = alpha;
     return EMO_OK;
@@ -197,15 +210,15 @@ __global__ void __launch_bounds__(256) compose_tile_kernel(const uint8_t *__rest
             *reinterpret_cast<uint2 *>(sm + (h1 / 3) * STRIDE + tile * RB + (h1 % 3) * 8) = make_uint2(v[k].z, v[k].w);
         }
     }
+    // make the generic-proxy shared-memory writes visible to the async proxy, then let the TMA engine
+    // stream every output row chunk (1536 contiguous bytes) to HBM: no LDS/STG on the LSU data pipe
+    fence_proxy_async_smem();
     __syncthreads();
     const size_t OWB = (size_t)bw * RB;
     uint8_t *d = out + (size_t)by * TS * OWB + (size_t)bx0 * RB;
-#pragma unroll
-    for (int k = 0; k < PIECES / 256; k++) {
-        const int p = threadIdx.x + 256 * k;
-        const int row = p / (ROW_CHUNK / 16), c16 = p % (ROW_CHUNK / 16);
-        const uint4 o = *reinterpret_cast<const uint4 *>(sm + row * STRIDE + c16 * 16);
-        stg_cs_v4(d + (size_t)row * OWB + c16 * 16, o);
+    if (threadIdx.x < TS) {
+        bulk_s2g(d + (size_t)threadIdx.x * OWB, sm + threadIdx.x * STRIDE, ROW_CHUNK);
+        bulk_commit_wait_read();  // shared memory must stay alive until the engine has read it
     }
 }
 
@@ -274,7 +287,8 @@ __global__ void __launch_bounds__(256) compose_tint_kernel(const uint8_t *__rest
                                                            uint32_t T, uint32_t ts, uint32_t dim, uint32_t bw,
                                                            const uint8_t *__restrict__ src, uint32_t W, uint32_t A,
                                                            uint32_t alpha_out, const uint8_t *__restrict__ excv,
-                                                           const uint8_t *__restrict__ excm, uint8_t *__restrict__ out,
+                                                           const uint8_t *__restrict__ excm,
+                                                           const uint8_t *__restrict__ cadd, uint8_t *__restrict__ out,
                                                            int *__restrict__ err) {
     const uint32_t gpr = ts / 4;                      // 4-pixel groups per tile row
     const uint32_t groups = bw * gpr;                 // per output row
@@ -296,8 +310,8 @@ __global__ void __launch_bounds__(256) compose_tint_kernel(const uint8_t *__rest
     for (uint32_t cr = 0; cr < dim; cr++) {
         const uint8_t *f = src + ((size_t)(by * dim + cr) * W + sx) * 3;
         const uint32_t fr = f[0], fg = f[1], fb = f[2];
-        const uint32_t c_rb = (fr * A + 1) | ((fb * A + 1) << 16);
-        const uint32_t c_ga = (fg * A + 1) | (alpha_out << 24);  // lane 1 = alpha_out * 256
+        const uint32_t c_rb = (fr * A + cadd[fr]) | ((fb * A + cadd[fb]) << 16);
+        const uint32_t c_ga = (fg * A + cadd[fg]) | (alpha_out << 24);  // lane 1 = alpha_out * 256
         uint32_t ew[K > 0 ? K : 1], mw[K > 0 ? K : 1];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -358,7 +372,7 @@ int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, ui
         dim3 grid((groups + 255) / 256, bh);
 #define EMO_TINT(KK)                                                                                                   \
     compose_tint_kernel<KK><<<grid, 256, 0, ctx->stream>>>(ctx->lib_px, item, T, ts, dim, bw, src, W, tint_alpha,       \
-                                                           t.alpha_out, t.excv, t.excm, out, ctx->err_flag)
+                                                           t.alpha_out, t.excv, t.excm, t.cadd, out, ctx->err_flag)
         switch (t.K) {
             case 0: EMO_TINT(0); break;
             case 1: EMO_TINT(1); break;

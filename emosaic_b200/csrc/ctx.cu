@@ -69,6 +69,7 @@ void emo_destroy(emo_ctx *ctx) {
     cudaFree(ctx->tint.lut);
     cudaFree(ctx->tint.excv);
     cudaFree(ctx->tint.excm);
+    cudaFree(ctx->tint.cadd);
     cudaFree(ctx->tint.meta);
     for (int i = 0; i < 4; i++)
         if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);

@@ -23,6 +23,19 @@ __global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed
                     a[i] = sad4(b[i], c, a[i]);  // VABSDIFF4.U8.ACC
                 } else if (WHICH == 2) {
                     a[i] = min(a[i], min(b[i], c + a[(i + 1) & 7]));  // VIMNMX3 (+ one IADD feeding it)
+                } else if (WHICH == 4) {
+                    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(a[i]) : "r"(b[i]), "r"(0x3c003c00u), "r"(a[i]));  // HFMA2
+                } else if (WHICH == 5) {
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(a[i]) : "r"(b[i]), "r"(a[i]));  // HADD2
+                } else if (WHICH == 6) {
+                    a[i] = sad4(b[i], c, a[i]);
+                    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(b[i]) : "r"(b[i]), "r"(0x3c003c00u), "r"(c));
+                } else if (WHICH == 7) {
+                    a[i] = sad4(b[i], c, a[i]);
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(b[i]) : "r"(b[i]), "r"(c));
+                } else if (WHICH == 8) {
+                    a[i] = sad4(b[i], c, a[i]);
+                    b[i] = b[i] * 65536u + c;  // IMAD
                 } else {
                     // the match inner loop: 4 x VABSDIFF4 + 2 x VIMNMX3 per (query, 4 candidates)
                     const uint32_t d0 = sad4(b[i], c, 0), d1 = sad4(b[i], c + 1, 0), d2 = sad4(b[i], c + 2, 0),
@@ -42,14 +55,14 @@ __global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed
 
 extern "C" int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s) {
     EMO_REQUIRE(ctx && inst_per_s, EMO_ERR_ARG, "emo_probe_int_pipe: NULL argument");
-    EMO_REQUIRE(which >= 0 && which <= 3, EMO_ERR_ARG, "emo_probe_int_pipe: which must be 0..3");
+    EMO_REQUIRE(which >= 0 && which <= 8, EMO_ERR_ARG, "emo_probe_int_pipe: which must be 0..8");
     EMO_CK(cudaSetDevice(ctx->device));
     int rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], 256);
     if (rc) return rc;
     uint32_t *out = (uint32_t *)ctx->stage[1];
     const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
     // thread-level instructions per iteration of the measured class(es)
-    const double per_iter = which == 3 ? 4.0 * 8 * 6 : (which == 2 ? 4.0 * 8 * 2 : 4.0 * 8);
+    const double per_iter = which == 3 ? 4.0 * 8 * 6 : ((which == 2 || which >= 6) ? 4.0 * 8 * 2 : 4.0 * 8);
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
         EMO_CK(cudaEventRecord(ctx->ev_start, ctx->stream));
@@ -57,7 +70,12 @@ extern "C" int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s) {
             case 0: probe_kernel<0><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
             case 1: probe_kernel<1><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
             case 2: probe_kernel<2><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            default: probe_kernel<3><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 3: probe_kernel<3><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 4: probe_kernel<4><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 5: probe_kernel<5><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 6: probe_kernel<6><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 7: probe_kernel<7><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            default: probe_kernel<8><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
         }
         EMO_LAUNCH_CHECK(ctx);
         EMO_CK(cudaEventRecord(ctx->ev_stop, ctx->stream));

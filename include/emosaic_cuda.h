@@ -138,7 +138,8 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
 /* ---- measurement helpers ------------------------------------------------------------------
  * Integer-pipe microbenchmark used as the roofline denominator of the match kernel:
  * dependent-free streams of VABSDIFF4 / VIMNMX3 / IMAD on every SM.
- * which: 0 = scalar INT32 (IMAD), 1 = VABSDIFF4.ACC, 2 = VIMNMX3, 3 = the match inner-loop mix
+ * which: 0 = scalar INT32 (IMAD), 1 = VABSDIFF4.ACC, 2 = VIMNMX3, 3 = the first match inner-loop mix,
+ * 4 = HFMA2, 5 = HADD2, 6 = VABSDIFF4+HFMA2, 7 = VABSDIFF4+HADD2, 8 = VABSDIFF4+IMAD (dual-pipe probes)
  * (4 VABSDIFF4 + 2 VIMNMX3).  Returns thread-level instructions per second. */
 int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s);
 
