@@ -1,0 +1,130 @@
+// cli.cpp — `emosaic` with the reference's command line (src/main.rs:28-138) for the accelerated path, C++ host.
+//   emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m 1|2|...|128|1to1|4to1|random] [-f] [-t X] [--extensions e ...]
+// Tiles and the source are decoded by the minimal PNG/PPM reader of emosaic.cpp and must already be tile_size x
+// tile_size (decode/trim/crop/Lanczos3 = prepare_tile is a host stage outside the accelerated path; the Python front
+// end `python -m emosaic_b200` does it with PIL, including JPEG).  Cache files are byte-compatible.
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+
+#include "emosaic.hpp"
+
+using namespace emosaic;
+
+static void find_images(const std::string &dir, const std::vector<std::string> &exts, std::vector<std::string> &out) {  // image.rs:7-23
+    std::vector<std::string> names;
+    if (DIR *d = opendir(dir.c_str())) {
+        while (dirent *e = readdir(d))
+            if (strcmp(e->d_name, ".") && strcmp(e->d_name, "..")) names.push_back(e->d_name);
+        closedir(d);
+    }
+    std::sort(names.begin(), names.end());
+    for (const std::string &n : names) {
+        const std::string p = dir + "/" + n;
+        struct stat st;
+        if (stat(p.c_str(), &st)) continue;
+        if (S_ISDIR(st.st_mode)) find_images(p, exts, out);
+        else {
+            const size_t dot = n.find_last_of('.');
+            if (dot != std::string::npos && std::find(exts.begin(), exts.end(), n.substr(dot + 1)) != exts.end()) out.push_back(p);
+        }
+    }
+}
+
+int main(int argc, char **argv) {
+    uint32_t tile_size = 16;
+    std::string output = "./output.jpg", img_path, tiles_dir, mode = "1";
+    bool crop = false, force = false, mosaic = false;
+    double tint = 0.0;
+    std::vector<std::string> exts = {"jpg", "jpeg"}, pos;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "error: %s needs a value\n", a.c_str()); exit(2); } return argv[++i]; };
+        if (a == "-s" || a == "--tile-size") tile_size = (uint32_t)std::stoul(next());
+        else if (a == "-o" || a == "--output-path") output = next();
+        else if (a == "--crop") crop = true;
+        else if (a == "-m" || a == "--mode") mode = next();
+        else if (a == "-f" || a == "--force") force = true;
+        else if (a == "-t" || a == "--tint-opacity") tint = std::stod(next());
+        else if (a == "--extensions") { exts.clear(); while (i + 1 < argc && argv[i + 1][0] != '-') exts.push_back(argv[++i]); }
+        else if (a == "--no-repeat" || a == "--randomize" || a == "--greedy" || a == "--html" || a == "--web") {
+            fprintf(stderr, "error: %s is outside the accelerated path\n", a.c_str());
+            return 2;
+        } else if (a == "mosaic") mosaic = true;
+        else pos.push_back(a);
+    }
+    if (!mosaic || pos.size() != 2) {
+        fprintf(stderr, "usage: emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m MODE] [-f] [-t X]\n");
+        return 2;
+    }
+    if (!(tint >= 0.0 && tint <= 1.0)) { fprintf(stderr, "error: Value must be between 0 and 1\n"); return 2; }
+    img_path = pos[0];
+    tiles_dir = pos[1];
+    try {
+        Context ctx(0);
+        const Image original = read_image(img_path);
+        uint32_t dim = mode == "1to1" ? 1 : mode == "4to1" ? 2 : mode == "random" ? 0 : (uint32_t)std::stoul(mode);
+        if (dim == 0) {  // random mode
+            std::vector<std::string> paths;
+            find_images(tiles_dir, exts, paths);
+            TileSet ts(1);
+            for (auto &p : paths) ts.push_tile_with_image(p, {0, 0, 0}, read_image(p));
+            fprintf(stderr, "Tile set with %zu tiles\n", ts.len());
+            write_png(output, render_random(ctx, original, ts, tile_size, 0));
+            return 0;
+        }
+        const uint32_t N = dim * dim;
+        auto [nw, nh] = adjust_dims(original.width, original.height, 1, dim);
+        if (nw != original.width || nh != original.height) {
+            fprintf(stderr, "Invalid source dimensions (%ux%u): Dimensions must be divisible by %u (resizing is a host stage)\n",
+                    original.width, original.height, dim);
+            return 1;
+        }
+        const std::string cache_path = tiles_dir + "/" + cache_file_name(N, crop);
+        TileSet ts(N);
+        bool have = false;
+        if (!force) {
+            std::ifstream f(cache_path, std::ios::binary);
+            if (f) {
+                std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+                try {
+                    TileSet cached = deserialize_tile_set(bytes, N, &exts, true);
+                    fprintf(stderr, "Reusing analysis cache\n");
+                    for (const Tile &t : cached.tiles()) ts.push_tile_with_image(cached.get_path(t), t.colors, read_image(cached.get_path(t)));
+                    have = true;
+                } catch (const Error &) {
+                }
+            }
+        }
+        if (!have) {  // generate_tile_set (main.rs:740-813): one batched analysis on the GPU
+            std::vector<std::string> paths;
+            find_images(tiles_dir, exts, paths);
+            std::vector<Image> tiles;
+            for (auto &p : paths) tiles.push_back(read_image(p));
+            const std::vector<uint8_t> colors = analyse_tiles(ctx, tiles, N);
+            for (size_t i = 0; i < paths.size(); i++)
+                ts.push_tile_with_image(paths[i], std::vector<uint8_t>(colors.begin() + i * N * 3, colors.begin() + (i + 1) * N * 3), tiles[i]);
+            const std::vector<uint8_t> blob = serialize_tile_set(ts);
+            std::ofstream(cache_path, std::ios::binary).write((const char *)blob.data(), blob.size());
+        }
+        fprintf(stderr, "Tile set with %zu tiles\n", ts.len());
+        RenderResult r = render_nto1(ctx, original, ts, tile_size, false, std::nullopt, tint);
+        if (tint > 0.0) {  // main.rs:447-478: RGBA PNG, early return
+            write_png(output, r.image);
+            return 0;
+        }
+        summarise(r, ts);
+        write_png(output, r.image);
+        const size_t dot = output.find_last_of('.');
+        write_png((dot == std::string::npos ? output : output.substr(0, dot)) + ".stats.png", render_stats(r, dim, tile_size));
+    } catch (const Error &e) {
+        fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

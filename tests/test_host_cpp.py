@@ -1,0 +1,89 @@
+"""The C++ host mirror (emosaic_b200/csrc/host): the reference's unit tests restated in C++ (host_tests) and the
+C++ `emosaic` command line end to end (PNG tiles) against the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "emosaic_b200")
+
+
+def _need(name):
+    p = os.path.join(BIN, name)
+    if not os.path.exists(p):
+        pytest.fail(f"{p} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    return p
+
+
+def test_host_tests_cpu_subset():
+    r = subprocess.run([_need("host_tests"), "--cpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "FAIL" not in r.stdout and r.stdout.count("PASS") >= 8
+
+
+@pytest.mark.gpu
+def test_host_tests_full():
+    r = subprocess.run([_need("host_tests")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "test_analyse_tiles_consistency_9" in r.stdout and "FAIL" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_cli_end_to_end(tmp_path):
+    import oracle
+    from emosaic_b200 import cache
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(4)
+    ts, T = 8, 50
+    tiles_dir = tmp_path / "tiles"
+    (tiles_dir / "b").mkdir(parents=True)
+    tiles, paths = [], []
+    for i in range(T):
+        img = np.clip(rng.integers(0, 256, 3) + rng.integers(-40, 41, (ts, ts, 3)), 0, 255).astype(np.uint8)
+        img[:, :3] //= 2
+        p = tiles_dir / ("b" if i % 4 == 0 else "") / f"t{i:02d}.png"
+        PIL.fromarray(img).save(p)
+        tiles.append(img)
+        paths.append(str(p))
+    order = np.argsort(_walk_order(str(tiles_dir), paths))
+    src = rng.integers(0, 256, (20, 28, 3), dtype=np.uint8)
+    PIL.fromarray(src).save(tmp_path / "src.png")
+    exe = _need("emosaic")
+    for mode, dim in (("1", 1), ("4to1", 2)):
+        out = tmp_path / f"out{dim}.png"
+        args = [exe, "-s", str(ts), "-o", str(out), str(tmp_path / "src.png"), "mosaic", str(tiles_dir), "-m", mode, "--extensions", "png"]
+        r = subprocess.run(args + ["-f"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        found = _find_images(str(tiles_dir))
+        px = np.stack([tiles[paths.index(p)] for p in found])
+        colors = oracle.analyse_tiles(px, dim * dim)
+        item, dist = oracle.match(colors, src)
+        assert (np.asarray(PIL.open(out)) == oracle.render(px, item)).all()
+        blob = (tiles_dir / cache.cache_file_name(dim * dim, False)).read_bytes()
+        assert blob == oracle.cache_serialize(colors, np.arange(1, T + 1), [None] * T, found)
+        assert "Average color distance" in r.stderr
+        # cache reuse + tint
+        r = subprocess.run(args + ["-t", "0.5"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "Reusing analysis cache" in r.stderr, r.stderr
+        got = np.asarray(PIL.open(out))
+        assert got.shape[2] == 4 and (got == oracle.tint(oracle.render(px, item), src, 127)).all()
+    r = subprocess.run([exe, "-s", "8", str(tmp_path / "src.png"), "mosaic", str(tiles_dir), "--no-repeat"], capture_output=True, text=True)
+    assert r.returncode == 2
+
+
+def _find_images(root):
+    out = []
+    for n in sorted(os.listdir(root)):
+        p = os.path.join(root, n)
+        if os.path.isdir(p):
+            out += _find_images(p)
+        elif n.endswith(".png"):
+            out.append(p)
+    return out
+
+
+def _walk_order(root, paths):
+    found = _find_images(root)
+    return [found.index(p) for p in paths]
