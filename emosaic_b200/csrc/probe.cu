@@ -33,6 +33,12 @@ __global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed
                 } else if (WHICH == 7) {
                     a[i] = sad4(b[i], c, a[i]);
                     asm("add.rn.f16x2 %0, %1, %2;" : "=r"(b[i]) : "r"(b[i]), "r"(c));
+                } else if (WHICH == 9) {
+                    asm("min.f16x2 %0, %1, %2;" : "=r"(a[i]) : "r"(a[i]), "r"(b[i]));  // HMNMX2
+                    b[i] += 0x00010001u;
+                } else if (WHICH == 10) {
+                    b[i] = sad4(b[i], c, a[i]);
+                    asm("min.f16x2 %0, %1, %2;" : "=r"(a[i]) : "r"(a[i]), "r"(b[i]));
                 } else if (WHICH == 8) {
                     a[i] = sad4(b[i], c, a[i]);
                     b[i] = b[i] * 65536u + c;  // IMAD
@@ -55,7 +61,7 @@ __global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed
 
 extern "C" int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s) {
     EMO_REQUIRE(ctx && inst_per_s, EMO_ERR_ARG, "emo_probe_int_pipe: NULL argument");
-    EMO_REQUIRE(which >= 0 && which <= 8, EMO_ERR_ARG, "emo_probe_int_pipe: which must be 0..8");
+    EMO_REQUIRE(which >= 0 && which <= 10, EMO_ERR_ARG, "emo_probe_int_pipe: which must be 0..10");
     EMO_CK(cudaSetDevice(ctx->device));
     int rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], 256);
     if (rc) return rc;
@@ -75,7 +81,9 @@ extern "C" int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s) {
             case 5: probe_kernel<5><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
             case 6: probe_kernel<6><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
             case 7: probe_kernel<7><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            default: probe_kernel<8><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 8: probe_kernel<8><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 9: probe_kernel<9><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            default: probe_kernel<10><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
         }
         EMO_LAUNCH_CHECK(ctx);
         EMO_CK(cudaEventRecord(ctx->ev_stop, ctx->stream));

@@ -324,6 +324,15 @@ def test_config4_stripe_and_properties(ctx):
     rows = rng.choice(512, 8, replace=False)
     for r in rows:
         assert (out[r * 8:(r + 1) * 8] == oracle.render(tiles, item[r:r + 1])).all()
+    # the full C4 match (4096 x 4096 queries x 100 000 tiles): L1 property on all 16.7 M blocks, stripe equality
+    full = np.random.default_rng(5678).integers(0, 256, (4096, 4096, 3), dtype=np.uint8)
+    fi, fd = ctx.match(full)
+    assert (fi[:512] == item).all() and (fd[:512] == dist).all()  # a stripe is just a smaller image
+    assert (fi > 0).all()
+    ch = colors[fi - 1, 0].astype(np.int16)
+    assert (np.abs(ch - full.astype(np.int16)).sum(-1, dtype=np.int64) == fd).all()
+    ri3, rd3 = kd.match(full[4000:4032])
+    assert (fi[4000:4032] == ri3).all() and (fd[4000:4032] == rd3).all()
     # idempotence: the library's own colours as the source
     self_src = colors[:4096 * 8, 0].reshape(8, 4096, 3)
     it, ds = ctx.match(self_src)
