@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) compose_copy_kernel(const uint8_t *__rest
 // tile as ONE contiguous run (192 / 768 B, 16-byte pieces), transposes through shared memory and writes
 // every output row chunk as 1536 contiguous bytes with 16-byte stores.
 template <int TS>
-__global__ void __launch_bounds__(256) compose_tile_kernel(const uint8_t *__restrict__ lib, const int32_t *__restrict__ item,
+__global__ void __launch_bounds__(192) compose_tile_kernel(const uint8_t *__restrict__ lib, const int32_t *__restrict__ item,
                                                            uint32_t T, uint32_t bw, uint8_t *__restrict__ out,
                                                            int *__restrict__ err) {
     constexpr int RB = TS * 3;                 // bytes per tile row
@@ -179,35 +179,34 @@ __global__ void __launch_bounds__(256) compose_tile_kernel(const uint8_t *__rest
     constexpr int G = 1536 / RB;               // tiles per CTA
     constexpr int ROW_CHUNK = G * RB;          // 1536
     constexpr int STRIDE = ROW_CHUNK + 16;     // padded shared-memory row stride (bank spread)
-    constexpr int PIECES = G * TILE_B / 16;    // 16-byte pieces per CTA (768 / 1536)
-    constexpr int PPT = TILE_B / 16;           // pieces per tile (12 / 48)
+    constexpr int PPT = TILE_B / 16;           // 16-byte pieces per tile (12 / 48)
+    constexpr int NTHR = 192;                  // a multiple of PPT: a thread keeps its piece index in every pass
+    constexpr int TPP = NTHR / PPT;            // tiles per pass (16 / 4)
+    constexpr int PASSES = G / TPP;            // 4 / 8
     __shared__ __align__(16) uint8_t sm[TS * STRIDE];
-    __shared__ uint32_t entries[G];
     const uint32_t by = blockIdx.y, bx0 = blockIdx.x * G;
-    if (threadIdx.x < G) {
+    const int part = threadIdx.x % PPT, tile0 = threadIdx.x / PPT;
+    const int32_t *it = item + (size_t)by * bw + bx0 + tile0;
+    uint4 v[PASSES];
+#pragma unroll
+    for (int k = 0; k < PASSES; k++) {
         uint32_t e = 0;
-        if (!item_to_entry(item[(size_t)by * bw + bx0 + threadIdx.x], T, e)) atomicOr(err, 1);
-        entries[threadIdx.x] = e;
+        if (!item_to_entry(__ldg(it + k * TPP), T, e)) atomicOr(err, 1);
+        v[k] = __ldg(reinterpret_cast<const uint4 *>(lib + (size_t)e * TILE_B + part * 16));
     }
-    __syncthreads();
-    uint4 v[PIECES / 256];
+    // shared-memory destination(s) of this thread's piece inside a tile: constant over the passes
+    uint8_t *dst = sm + tile0 * RB;
+    if constexpr (RB % 16 == 0) {
+        dst += ((part * 16) / RB) * STRIDE + (part * 16) % RB;
 #pragma unroll
-    for (int k = 0; k < PIECES / 256; k++) {
-        const int p = threadIdx.x + 256 * k;
-        const int tile = p / PPT, part = p % PPT;
-        v[k] = __ldg(reinterpret_cast<const uint4 *>(lib + (size_t)entries[tile] * TILE_B + part * 16));
-    }
+        for (int k = 0; k < PASSES; k++) *reinterpret_cast<uint4 *>(dst + k * TPP * RB) = v[k];
+    } else {  // RB = 24: the piece straddles rows at 8-byte granularity
+        const int h0 = 2 * part, h1 = 2 * part + 1;
+        uint8_t *d0 = dst + (h0 / 3) * STRIDE + (h0 % 3) * 8, *d1 = dst + (h1 / 3) * STRIDE + (h1 % 3) * 8;
 #pragma unroll
-    for (int k = 0; k < PIECES / 256; k++) {
-        const int p = threadIdx.x + 256 * k;
-        const int tile = p / PPT, part = p % PPT;
-        if constexpr (RB % 16 == 0) {
-            const int row = (part * 16) / RB, col = (part * 16) % RB;
-            *reinterpret_cast<uint4 *>(sm + row * STRIDE + tile * RB + col) = v[k];
-        } else {  // RB = 24: the piece straddles rows at 8-byte granularity
-            const int h0 = 2 * part, h1 = 2 * part + 1;
-            *reinterpret_cast<uint2 *>(sm + (h0 / 3) * STRIDE + tile * RB + (h0 % 3) * 8) = make_uint2(v[k].x, v[k].y);
-            *reinterpret_cast<uint2 *>(sm + (h1 / 3) * STRIDE + tile * RB + (h1 % 3) * 8) = make_uint2(v[k].z, v[k].w);
+        for (int k = 0; k < PASSES; k++) {
+            *reinterpret_cast<uint2 *>(d0 + k * TPP * RB) = make_uint2(v[k].x, v[k].y);
+            *reinterpret_cast<uint2 *>(d1 + k * TPP * RB) = make_uint2(v[k].z, v[k].w);
         }
     }
     // make the generic-proxy shared-memory writes visible to the async proxy, then let the TMA engine
@@ -339,9 +338,9 @@ int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, ui
     const bool aligned = ((uintptr_t)out % 16 == 0) && bh <= 65535;
     if (oc == 3) {
         if (aligned && ts == 8 && bw % 64 == 0) {
-            compose_tile_kernel<8><<<dim3(bw / 64, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
+            compose_tile_kernel<8><<<dim3(bw / 64, bh), 192, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
         } else if (aligned && ts == 16 && bw % 32 == 0) {
-            compose_tile_kernel<16><<<dim3(bw / 32, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
+            compose_tile_kernel<16><<<dim3(bw / 32, bh), 192, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
         } else if (aligned && RB % 16 == 0) {
             const uint32_t pieces = bw * RB / 16;
             compose_copy_kernel<uint4><<<dim3((pieces + 255) / 256, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, ts, bw, out,

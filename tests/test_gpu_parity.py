@@ -354,6 +354,25 @@ def test_config5_tint_large(ctx):
     assert (out == oracle.tint(oracle.render(tiles, item), src, 127)).all()
 
 
+def test_config5_full_size(ctx):
+    """C5 at full size: 4096 tiles of 32x32, 1024x1024 source, A = 127 -> 32768 x 32768 x 4 (4.29 GB, offsets beyond
+    2^32).  Maps equal the KD-tree oracle everywhere; composited + tinted rows equal the oracle on sampled block rows."""
+    rng = np.random.default_rng(1234)
+    tiles = rng.integers(0, 256, (4096, 32, 32, 3), dtype=np.uint8)
+    src = np.random.default_rng(5678).integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+    colors = ctx.analyse_tiles(tiles, 1)
+    ctx.set_library(colors, tiles)
+    out, item, dist = ctx.mosaic(src, 4, 127)
+    assert out.shape == (32768, 32768, 4)
+    ri, rd = oracle.KdTree(colors).match(src)
+    assert (item == ri).all() and (dist == rd).all()
+    for r in (0, 1, 511, 777, 1022, 1023):
+        want = oracle.tint(oracle.render(tiles, ri[r:r + 1]), src[r:r + 1], 127)
+        assert (out[r * 32:(r + 1) * 32] == want).all(), r
+    assert (out[..., 3] == 255).all()
+    del out
+
+
 def test_mosaic_chunked_pipeline_matches_single_calls(ctx):
     """emo_mosaic pipelines block-row chunks; result must equal match + compose done in one piece."""
     rng = np.random.default_rng(2)
