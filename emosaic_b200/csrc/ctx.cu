@@ -444,8 +444,12 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
     const uint32_t dim = ctx->dim, ts = ctx->ts, bw = W / dim, bh = H / dim;
     const size_t Q = (size_t)bw * bh, sb = (size_t)W * H * 3;
     const size_t row_out = (size_t)bw * ts * ts * oc;  // output bytes per block row
-    // chunk: ~64 MB of output per step, at least one block row
+    // chunk: ~64 MB of output per step, but at least ~1.2 M queries (the match kernel needs that many to fill
+    // the GPU without splitting the candidate range) as long as that still leaves >= 8 chunks to overlap the
+    // D2H of one chunk with the kernels of the next; at least one block row
     uint32_t rows_per_chunk = (uint32_t)((64ull << 20) / (row_out ? row_out : 1));
+    const uint32_t rows_for_q = ((1200000u + bw - 1) / bw);
+    if (rows_per_chunk < rows_for_q && rows_for_q * 8 <= bh) rows_per_chunk = rows_for_q;
     if (rows_per_chunk < 1) rows_per_chunk = 1;
     if (rows_per_chunk > bh) rows_per_chunk = bh;
     const size_t chunk_out = row_out * rows_per_chunk;
