@@ -80,6 +80,36 @@ def test_analyse_full_size_properties(ctx):
     assert (o1[:, 0] == tot.astype(np.uint8)).all()
 
 
+def test_config3_full_size_device_api(ctx):
+    """C3 at full size through the device-pointer ABI (the way bench.py drives it): 1 000 000 tiles of 64x64
+    (12.29 GB) generated in HBM with torch, fused 1to1 + 4to1 analysis, oracle parity on 3 000 sampled tiles and
+    the exact identity mean1 = floor(sum of the four quadrant sums / 4096) checked against separate dim=1 / dim=2 runs."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    T = 1_000_000
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    tiles = torch.randint(0, 256, (T, 64, 64, 3), dtype=torch.uint8, device=dev, generator=g)
+    tiles[0] = 255
+    tiles[1] = 0
+    o1 = torch.empty((T, 1, 3), dtype=torch.uint8, device=dev)
+    o4 = torch.empty((T, 4, 3), dtype=torch.uint8, device=dev)
+    s1 = torch.empty_like(o1)
+    s4 = torch.empty_like(o4)
+    torch.cuda.synchronize()
+    ctx.analyse_fused_dev(tiles.data_ptr(), T, 64, o1.data_ptr(), o4.data_ptr())
+    ctx.analyse_dev(tiles.data_ptr(), T, 64, 1, s1.data_ptr())
+    ctx.analyse_dev(tiles.data_ptr(), T, 64, 2, s4.data_ptr())
+    ctx.sync()
+    assert bool((o1 == s1).all()) and bool((o4 == s4).all())
+    sel = torch.cat([torch.arange(0, 1000, device=dev), torch.randint(0, T, (2000,), device=dev, generator=g)])
+    th = tiles[sel].cpu().numpy()
+    assert (o1[sel].cpu().numpy() == oracle.analyse_tiles(th, 1)).all()
+    assert (o4[sel].cpu().numpy() == oracle.analyse_tiles(th, 4)).all()
+    assert o1[0].tolist() == [[255, 255, 255]] and o4[1].tolist() == [[0, 0, 0]] * 4
+    del tiles
+
+
 # ---- match ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,T,H,W", [(1, 300, 100, 100), (1, 4096, 100, 100), (1, 1, 3, 5), (1, 17, 1, 1), (4, 500, 64, 96),
                                      (4, 10000, 128, 128), (9, 200, 30, 42), (16, 100, 16, 24), (1, 33000, 64, 64),
