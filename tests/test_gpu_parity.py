@@ -415,3 +415,50 @@ def test_mosaic_chunked_pipeline_matches_single_calls(ctx):
     assert (item == i2).all() and (dist == d2).all()
     o2 = ctx.compose(i2)
     assert sha(out) == sha(o2)
+
+
+# ---- out-of-bounds write audit (compute-sanitizer is closed on this pool): canaries around every output -------
+def _guarded(torch, nbytes, dev, pad=4096):
+    buf = torch.full((pad + nbytes + pad,), 0xA5, dtype=torch.uint8, device=dev)
+    return buf, buf.data_ptr() + pad, pad
+
+
+def _intact(torch, buf, nbytes, pad):
+    return bool((buf[:pad] == 0xA5).all()) and bool((buf[pad + nbytes:] == 0xA5).all())
+
+
+@pytest.mark.parametrize("N,ts,T,bh,bw", [(1, 8, 300, 5, 64), (1, 8, 300, 3, 7), (1, 16, 200, 4, 32), (4, 16, 100, 3, 5), (1, 32, 50, 2, 9),
+                                          (9, 12, 60, 2, 3), (1, 64, 20, 1, 2), (25, 10, 40, 2, 3)])
+def test_no_out_of_bounds_writes(ctx, N, ts, T, bh, bw):
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    dim = int(N ** 0.5)
+    rng = np.random.default_rng(N * 100 + ts)
+    tiles_h = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    src_h = rng.integers(0, 256, (bh * dim, bw * dim, 3), dtype=np.uint8)
+    tiles = torch.from_numpy(tiles_h).to(dev)
+    src = torch.from_numpy(src_h).to(dev)
+    Q = bh * bw
+    cbuf, cptr, pad = _guarded(torch, T * N * 3, dev)
+    ibuf, iptr, _ = _guarded(torch, Q * 4, dev)
+    dbuf, dptr, _ = _guarded(torch, Q * 4, dev)
+    obuf, optr, _ = _guarded(torch, Q * ts * ts * 3, dev)
+    tbuf, tptr, _ = _guarded(torch, Q * ts * ts * 4, dev)
+    torch.cuda.synchronize()
+    ctx.analyse_dev(tiles.data_ptr(), T, ts, dim, cptr)
+    ctx.set_library_dev(cptr, tiles.data_ptr(), T, N, ts)
+    ctx.match_dev(src.data_ptr(), bw * dim, bh * dim, iptr, dptr)
+    ctx.compose_dev(iptr, 0, bw * dim, bh * dim, 3, 0, optr)
+    ctx.compose_dev(iptr, src.data_ptr(), bw * dim, bh * dim, 4, 127, tptr)
+    ctx.sync()
+    for buf, n in ((cbuf, T * N * 3), (ibuf, Q * 4), (dbuf, Q * 4), (obuf, Q * ts * ts * 3), (tbuf, Q * ts * ts * 4)):
+        assert _intact(torch, buf, n, pad)
+    colors = cbuf[pad:pad + T * N * 3].cpu().numpy().reshape(T, N, 3)
+    assert (colors == oracle.analyse_tiles(tiles_h, N)).all()
+    ri, rd = oracle.match(colors, src_h)
+    item = ibuf[pad:pad + Q * 4].cpu().numpy().view(np.int32).reshape(bh, bw)
+    assert (item == ri).all()
+    out = obuf[pad:pad + Q * ts * ts * 3].cpu().numpy().reshape(bh * ts, bw * ts, 3)
+    assert (out == oracle.render(tiles_h, ri)).all()
+    tint = tbuf[pad:pad + Q * ts * ts * 4].cpu().numpy().reshape(bh * ts, bw * ts, 4)
+    assert (tint == oracle.tint(out, src_h, 127)).all()
