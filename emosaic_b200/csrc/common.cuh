@@ -65,7 +65,7 @@ struct emo_ctx {
     // resident library
     uint32_t T = 0, N = 0, dim = 0, ts = 0;
     uint32_t words = 0;       // packed u32 words per candidate vector = ceil(3N/4)
-    bool wide = false;        // N outside {1,4,9,16}: vectors padded to a multiple of 32 words, match_wide_kernel
+    bool wide = false;        // N outside {1,4,9,16}: vectors padded to a multiple of 8 words, match_wide_kernel
     uint32_t *qvec = nullptr; // wide path scratch: packed query vectors [Qpad][words]
     size_t qvec_cap = 0;
     uint32_t L = 0;           // real candidates (T for N==1, 2T otherwise)

@@ -297,9 +297,9 @@ static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, boo
     while (dim * dim < N) dim++;
     uint32_t words = (3 * N + 3) / 4;
     // --mode 1..4 (N = 1, 4, 9, 16) keep the query vectors in registers; larger N (--mode 5..128, up to
-    // 49 152 bytes per vector) use the tiled wide kernel with vectors padded to a multiple of 32 words.
+    // 49 152 bytes per vector) use the tiled wide kernel with vectors padded to a multiple of 8 words.
     ctx->wide = !(words == 1 || words == 3 || words == 7 || words == 12);
-    if (ctx->wide) words = (words + 31) / 32 * 32;
+    if (ctx->wide) words = (words + 7) / 8 * 8;
     if ((uint64_t)N * 3 * 255 >= (1ull << 32)) {
         emo_set_error("set_library: N=%u overflows the u32 distance", N);
         return EMO_ERR_UNSUPPORTED;

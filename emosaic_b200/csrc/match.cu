@@ -385,49 +385,80 @@ __global__ void pack_queries_kernel(const uint8_t *__restrict__ src, uint32_t W,
 __global__ void __launch_bounds__(256) match_wide_kernel(const uint32_t *__restrict__ qvec, const uint32_t *__restrict__ cand,
                                                          uint32_t words, uint32_t n_ctiles, uint32_t tiles_per_split, uint32_t Q,
                                                          unsigned long long *__restrict__ keys) {
-    __shared__ __align__(16) uint32_t sq[WK][WQ];
-    __shared__ __align__(16) uint32_t sc[WK][WC];
+    // double-buffered slices: the global loads of slice i+1 are in flight while slice i is consumed
+    __shared__ __align__(16) uint32_t sq[2][WK][WQ];
+    __shared__ __align__(16) uint32_t sc[2][WK][WC];
     const int tid = threadIdx.x, tq = tid >> 4, tc = tid & 15;
     const uint32_t q0 = blockIdx.x * WQ;
     const uint32_t t0 = blockIdx.y * tiles_per_split, t1 = min(t0 + tiles_per_split, n_ctiles);
     uint32_t bestd[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, besti[4] = {0, 0, 0, 0};
     // loader mapping: thread -> (row = tid / 8 (+32), quad = tid % 8): 4 consecutive words of one vector
     const int lrow = tid >> 3, lquad = tid & 7;
-    for (uint32_t t = t0; t < t1; t++) {
-        uint32_t acc[4][4];
+    const uint32_t n_slices = (words + WK - 1) / WK;          // words is a multiple of 8; the last slice may be short
+    const uint32_t n_steps = (t1 - t0) * n_slices;
+    uint4 vq[2], vc[2];
+    auto fetch = [&](uint32_t step) {
+        const uint32_t t = t0 + step / n_slices, k = (step % n_slices) * WK + lquad * 4;
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = 0;
-        for (uint32_t k0 = 0; k0 < words; k0 += WK) {
-            __syncthreads();
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int row = lrow + 32 * h;
-                const uint4 vq = __ldg(reinterpret_cast<const uint4 *>(qvec + (size_t)(q0 + row) * words + k0 + lquad * 4));
-                const uint4 vc = __ldg(reinterpret_cast<const uint4 *>(cand + ((size_t)t * WC + row) * words + k0 + lquad * 4));
-                const int col = row ^ (lquad << 2);  // swizzle: word rows 4*lquad..+3 share this column permutation
-                sq[lquad * 4 + 0][col] = vq.x; sq[lquad * 4 + 1][col] = vq.y; sq[lquad * 4 + 2][col] = vq.z; sq[lquad * 4 + 3][col] = vq.w;
-                sc[lquad * 4 + 0][col] = vc.x; sc[lquad * 4 + 1][col] = vc.y; sc[lquad * 4 + 2][col] = vc.z; sc[lquad * 4 + 3][col] = vc.w;
-            }
-            __syncthreads();
-#pragma unroll 8
-            for (int k = 0; k < WK; k++) {
-                const int sw = (k >> 2) & 7;
-                const uint4 a4 = *reinterpret_cast<const uint4 *>(&sq[k][(tq ^ sw) * 4]);
-                const uint4 c4 = *reinterpret_cast<const uint4 *>(&sc[k][(tc ^ sw) * 4]);
-                const uint32_t qa[4] = {a4.x, a4.y, a4.z, a4.w}, cb[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int b = 0; b < 4; b++) acc[a][b] = sad4(qa[a], cb[b], acc[a][b]);
+        for (int h = 0; h < 2; h++) {
+            const int row = lrow + 32 * h;
+            if (k < words) {
+                vq[h] = __ldg(reinterpret_cast<const uint4 *>(qvec + (size_t)(q0 + row) * words + k));
+                vc[h] = __ldg(reinterpret_cast<const uint4 *>(cand + ((size_t)t * WC + row) * words + k));
+            } else {
+                vq[h] = make_uint4(0, 0, 0, 0);
+                vc[h] = make_uint4(0, 0, 0, 0);
             }
         }
+    };
+    auto stash = [&](int buf) {
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int h = 0; h < 2; h++) {
+            const int col = (lrow + 32 * h) ^ (lquad << 2);  // swizzle: word rows 4*lquad..+3 share this column permutation
+            sq[buf][lquad * 4 + 0][col] = vq[h].x; sq[buf][lquad * 4 + 1][col] = vq[h].y;
+            sq[buf][lquad * 4 + 2][col] = vq[h].z; sq[buf][lquad * 4 + 3][col] = vq[h].w;
+            sc[buf][lquad * 4 + 0][col] = vc[h].x; sc[buf][lquad * 4 + 1][col] = vc[h].y;
+            sc[buf][lquad * 4 + 2][col] = vc[h].z; sc[buf][lquad * 4 + 3][col] = vc[h].w;
+        }
+    };
+    uint32_t acc[4][4];
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (acc[a][b] < bestd[a]) { bestd[a] = acc[a][b]; besti[a] = t * WC + tc * 4 + b; }
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0;
+    if (n_steps) {
+        fetch(0);
+        stash(0);
+    }
+    __syncthreads();
+    for (uint32_t step = 0; step < n_steps; step++) {
+        const int buf = step & 1;
+        if (step + 1 < n_steps) fetch(step + 1);
+        const uint32_t sl = step % n_slices;
+        const int kmax = (int)min((uint32_t)WK, words - sl * WK);
+#pragma unroll 8
+        for (int k = 0; k < kmax; k++) {
+            const int sw = (k >> 2) & 7;
+            const uint4 a4 = *reinterpret_cast<const uint4 *>(&sq[buf][k][(tq ^ sw) * 4]);
+            const uint4 c4 = *reinterpret_cast<const uint4 *>(&sc[buf][k][(tc ^ sw) * 4]);
+            const uint32_t qa[4] = {a4.x, a4.y, a4.z, a4.w}, cb[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] = sad4(qa[a], cb[b], acc[a][b]);
+        }
+        if (sl == n_slices - 1) {  // tile finished: fold, candidates in increasing rank, strict `<`
+            const uint32_t t = t0 + step / n_slices;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (acc[a][b] < bestd[a]) { bestd[a] = acc[a][b]; besti[a] = t * WC + tc * 4 + b; }
+                    acc[a][b] = 0;
+                }
+        }
+        if (step + 1 < n_steps) stash(buf ^ 1);
+        __syncthreads();
     }
     // merge the 16 lanes that share a query group (lexicographic (dist, rank) minimum), then across splits
 #pragma unroll
