@@ -462,3 +462,31 @@ def test_no_out_of_bounds_writes(ctx, N, ts, T, bh, bw):
     assert (out == oracle.render(tiles_h, ri)).all()
     tint = tbuf[pad:pad + Q * ts * ts * 4].cpu().numpy().reshape(bh * ts, bw * ts, 4)
     assert (tint == oracle.tint(out, src_h, 127)).all()
+
+
+def test_random_geometry_sweep(ctx):
+    """80 seeded random geometries (mode, tile size, library size, source shape, alpha) through the whole path."""
+    rng = np.random.default_rng(20260101)
+    for case in range(80):
+        dim = int(rng.choice([1, 1, 1, 2, 2, 3, 4, 5]))
+        N = dim * dim
+        ts = dim * int(rng.integers(1, 9)) if dim > 1 else int(rng.choice([1, 2, 3, 4, 5, 8, 8, 12, 16, 16, 32]))
+        T = int(rng.choice([1, 2, 7, 64, 129, 300, 1000, 2049]))
+        bh, bw = int(rng.integers(1, 12)), int(rng.choice([1, 3, 8, 32, 33, 64, 65]))
+        A = int(rng.choice([0, 1, 60, 85, 127, 128, 200, 254, 255]))
+        tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+        if case % 3 == 0:  # few distinct colours: many exact ties
+            tiles = (tiles // 128 * 128).astype(np.uint8)
+        src = rng.integers(0, 256, (bh * dim, bw * dim, 3), dtype=np.uint8)
+        if case % 3 == 0:
+            src = (src // 128 * 128).astype(np.uint8)
+        tag = f"case {case}: N={N} ts={ts} T={T} blocks={bh}x{bw} A={A}"
+        colors = ctx.analyse_tiles(tiles, dim)
+        assert (colors == oracle.analyse_tiles(tiles, N)).all(), tag
+        ctx.set_library(colors, tiles)
+        out, item, dist = ctx.mosaic(src, 4, A)
+        ri, rd = oracle.match(colors, src)
+        assert (item == ri).all() and (dist == rd).all(), tag
+        rgb = oracle.render(tiles, ri)
+        assert (out == oracle.tint(rgb, src, A)).all(), tag
+        assert (ctx.compose(item) == rgb).all(), tag
