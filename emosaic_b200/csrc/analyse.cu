@@ -12,7 +12,7 @@
 // Roofline: pure HBM read stream, 3*ts*ts bytes in per tile, 3*N bytes out
 // (12 288 + 15 B per tile for the fused 1to1+4to1 pass at ts=64).
 //
-// Fast kernel (ts = 32 or 64): one warp owns a private ring of shared-memory stages, lane 0
+// Fast kernels (ts = 8, 16, 32, 64): one warp owns a private ring of shared-memory stages, lane 0
 // feeds it with TMA 1-D bulk copies (cp.async.bulk, completion on an mbarrier), so the only
 // global-memory instructions in the kernel are a handful of bulk copies per warp and ~4 KB..6 KB
 // per stage are in flight per warp (>= 144 KB per SM).  A stage is a run of 32 tile rows; lanes
@@ -191,14 +191,126 @@ static int launch_fast(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint8_t *
     return EMO_OK;
 }
 
-static bool fast_ok(const uint8_t *tiles, uint32_t ts) { return (ts == 32 || ts == 64) && ((uintptr_t)tiles % 16 == 0); }
+// ---------------------------------------------------------------------------------------
+// small tiles (ts = 8, 16 — the reference's default tile size is 16): same per-warp TMA ring, but a stage
+// (1536 B = 32 groups of 48 B, one group per lane) holds 8 / 2 whole tiles
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sum12(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &r, uint32_t &g, uint32_t &b) {
+    // one 12-byte run = 4 pixels: (r g b r)(g b r g)(b r g b)
+    r = __dp4a(w0, 0x01000001u, r); g = __dp4a(w0, 0x00000100u, g); b = __dp4a(w0, 0x00010000u, b);
+    r = __dp4a(w1, 0x00010000u, r); g = __dp4a(w1, 0x01000001u, g); b = __dp4a(w1, 0x00000100u, b);
+    r = __dp4a(w2, 0x00000100u, r); g = __dp4a(w2, 0x00010000u, g); b = __dp4a(w2, 0x01000001u, b);
+}
+
+template <int TS, bool OUT1, bool OUT4>
+__global__ void __launch_bounds__(512, 1)
+analyse_small_kernel(const uint8_t *__restrict__ tiles, uint64_t T, uint8_t *__restrict__ out1, uint8_t *__restrict__ out4) {
+    constexpr int STAGE_BYTES = 1536, STAGES = 8, WARPS = 16;
+    constexpr int TILE_BYTES = TS * TS * 3;            // 768 / 192
+    constexpr int TPS = STAGE_BYTES / TILE_BYTES;      // tiles per stage: 2 / 8
+    constexpr int LPT = 32 / TPS;                      // lanes per tile: 16 / 4
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *ring = smem + (size_t)warp * STAGES * STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * STAGES * STAGE_BYTES) + warp * STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const uint64_t n_stage_total = (T + TPS - 1) / TPS;                 // stages in the whole library
+    const uint64_t gw = (uint64_t)blockIdx.x * WARPS + warp, nw = (uint64_t)gridDim.x * WARPS;
+    const uint64_t my = n_stage_total > gw ? (n_stage_total - gw + nw - 1) / nw : 0;
+    auto issue = [&](uint64_t n) {  // lane 0: bulk-load this warp's n-th stage (the last stage of the library may be short)
+        const uint64_t st = gw + n * nw, first = st * TPS;
+        const uint32_t bytes = (uint32_t)((T - first < (uint64_t)TPS ? T - first : (uint64_t)TPS) * TILE_BYTES);
+        const int s = (int)(n % STAGES);
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        bulk_g2s(ring + (size_t)s * STAGE_BYTES, tiles + first * TILE_BYTES, bytes, &bars[s]);
+    };
+    if (lane == 0)
+        for (uint64_t n = 0; n < (uint64_t)(STAGES - 1) && n < my; n++) issue(n);
+    for (uint64_t n = 0; n < my; n++) {
+        if (lane == 0 && n + STAGES - 1 < my) issue(n + STAGES - 1);
+        const int s = (int)(n % STAGES);
+        mbar_wait(&bars[s], (uint32_t)((n / STAGES) & 1));
+        const uint4 *p = reinterpret_cast<const uint4 *>(ring + (size_t)s * STAGE_BYTES + lane * 48);
+        const uint64_t tile = (gw + n * nw) * TPS + lane / LPT;
+        uint32_t L[3] = {0, 0, 0}, Rr[3] = {0, 0, 0};  // left / right cell column of this lane's 48-byte group
+        if (tile < T) {  // a short last stage leaves stale bytes behind the valid tiles
+            const uint4 a = p[0], b = p[1], c = p[2];
+            if (TS == 16) {  // group = one 16-pixel row: pixels 0-7 | 8-15
+                sum12(a.x, a.y, a.z, L[0], L[1], L[2]);  sum12(a.w, b.x, b.y, L[0], L[1], L[2]);
+                sum12(b.z, b.w, c.x, Rr[0], Rr[1], Rr[2]); sum12(c.y, c.z, c.w, Rr[0], Rr[1], Rr[2]);
+            } else {         // group = two 8-pixel rows: (row0: 0-3 | 4-7) (row1: 0-3 | 4-7)
+                sum12(a.x, a.y, a.z, L[0], L[1], L[2]);  sum12(a.w, b.x, b.y, Rr[0], Rr[1], Rr[2]);
+                sum12(b.z, b.w, c.x, L[0], L[1], L[2]);  sum12(c.y, c.z, c.w, Rr[0], Rr[1], Rr[2]);
+            }
+        }
+        __syncwarp();
+        // lanes of one cell row: TS=16 -> 8 consecutive lanes (rows), TS=8 -> 2 consecutive lanes (row pairs)
+        constexpr int CR_LANES = LPT / 2;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+#pragma unroll
+            for (int m = 1; m < CR_LANES; m <<= 1) {
+                L[ch] += __shfl_xor_sync(0xffffffffu, L[ch], m);
+                Rr[ch] += __shfl_xor_sync(0xffffffffu, Rr[ch], m);
+            }
+        }
+        constexpr uint32_t CELL_PX = (TS / 2) * (TS / 2);
+        const int crow = (lane / CR_LANES) & 1;
+        if (OUT4 && tile < T && (lane % CR_LANES) == 0) {
+            uint8_t *o = out4 + tile * 12 + crow * 6;
+            o[0] = (uint8_t)(L[0] / CELL_PX); o[1] = (uint8_t)(L[1] / CELL_PX); o[2] = (uint8_t)(L[2] / CELL_PX);
+            o[3] = (uint8_t)(Rr[0] / CELL_PX); o[4] = (uint8_t)(Rr[1] / CELL_PX); o[5] = (uint8_t)(Rr[2] / CELL_PX);
+        }
+        if (OUT1) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                uint32_t v = L[ch] + Rr[ch];
+                v += __shfl_xor_sync(0xffffffffu, v, CR_LANES);  // the other cell row of the tile
+                L[ch] = v / (uint32_t)(TS * TS);
+            }
+            if (tile < T && (lane % LPT) == 0) {
+                uint8_t *o = out1 + tile * 3;
+                o[0] = (uint8_t)L[0]; o[1] = (uint8_t)L[1]; o[2] = (uint8_t)L[2];
+            }
+        }
+    }
+}
+
+template <int TS, bool OUT1, bool OUT4>
+static int launch_small(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint8_t *out1, uint8_t *out4) {
+    auto kern = analyse_small_kernel<TS, OUT1, OUT4>;
+    const size_t smem = (size_t)16 * 8 * 1536 + 16 * 8 * 8 + 128;
+    EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t stages = (T * (TS * TS * 3) + 1535) / 1536, want = (stages + 15) / 16;
+    const int grid = (int)(want < (uint64_t)ctx->sm_count ? want : (uint64_t)ctx->sm_count);
+    kern<<<grid, 512, smem, ctx->stream>>>(tiles, T, out1, out4);
+    EMO_LAUNCH_CHECK(ctx);
+    return EMO_OK;
+}
+
+template <bool OUT1, bool OUT4>
+static int launch_any_fast(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
+    switch (ts) {
+        case 64: return launch_fast<64, OUT1, OUT4>(ctx, tiles, T, out1, out4);
+        case 32: return launch_fast<32, OUT1, OUT4>(ctx, tiles, T, out1, out4);
+        case 16: return launch_small<16, OUT1, OUT4>(ctx, tiles, T, out1, out4);
+        default: return launch_small<8, OUT1, OUT4>(ctx, tiles, T, out1, out4);
+    }
+}
+
+static bool fast_ok(const uint8_t *tiles, uint32_t ts) {
+    return (ts == 8 || ts == 16 || ts == 32 || ts == 64) && ((uintptr_t)tiles % 16 == 0);
+}
 
 int emo_launch_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out) {
     if (fast_ok(tiles, ts) && (dim == 1 || dim == 2)) {
-        if (ts == 64) return dim == 1 ? launch_fast<64, true, false>(ctx, tiles, T, out, nullptr)
-                                      : launch_fast<64, false, true>(ctx, tiles, T, nullptr, out);
-        return dim == 1 ? launch_fast<32, true, false>(ctx, tiles, T, out, nullptr)
-                        : launch_fast<32, false, true>(ctx, tiles, T, nullptr, out);
+        return dim == 1 ? launch_any_fast<true, false>(ctx, tiles, T, ts, out, nullptr)
+                        : launch_any_fast<false, true>(ctx, tiles, T, ts, nullptr, out);
     }
     uint64_t total = T * dim * dim;
     uint64_t blocks = (total + 255) / 256;
@@ -209,10 +321,7 @@ int emo_launch_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t 
 }
 
 int emo_launch_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
-    if (fast_ok(tiles, ts)) {
-        return ts == 64 ? launch_fast<64, true, true>(ctx, tiles, T, out1, out4)
-                        : launch_fast<32, true, true>(ctx, tiles, T, out1, out4);
-    }
+    if (fast_ok(tiles, ts)) return launch_any_fast<true, true>(ctx, tiles, T, ts, out1, out4);
     int rc = emo_launch_analyse(ctx, tiles, T, ts, 1, out1);
     if (rc) return rc;
     return emo_launch_analyse(ctx, tiles, T, ts, 2, out4);
