@@ -307,7 +307,7 @@ static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, boo
     ctx->T = T; ctx->N = N; ctx->dim = dim; ctx->ts = ts; ctx->words = words;
     ctx->L = (N == 1) ? T : 2 * T;  // for N == 1 a tile and its mirror coincide; the mirror can never win a tie
     uint32_t chunk = (words == 1) ? 1024 : (words == 3 ? 512 : 256);
-    if (ctx->wide) chunk = 64;  // candidate tile of match_wide_kernel
+    if (ctx->wide) chunk = 128;  // candidate tile of match_wide_kernel
     uint32_t lwin = (ctx->L + 127) / 128 * 128;  // stages are scanned in windows of 128 candidates (MATCH_WIN)
     if (lwin < chunk && !ctx->wide) chunk = lwin;
     ctx->chunk = chunk;

@@ -81,11 +81,17 @@ __global__ void build_pixels_kernel(const uint8_t *__restrict__ px, uint32_t T, 
     }
 }
 
+int emo_launch_tile_candidates(emo_ctx *ctx);
+
 int emo_launch_build_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px) {
     const uint32_t Lpad = ctx->n_chunks * ctx->chunk;
     build_candidates_kernel<<<(Lpad + 255) / 256, 256, 0, ctx->stream>>>(colors, ctx->T, ctx->N, ctx->dim, ctx->words, ctx->L,
                                                                         Lpad, ctx->cand);
     EMO_LAUNCH_CHECK(ctx);
+    if (ctx->wide) {
+        int rc = emo_launch_tile_candidates(ctx);
+        if (rc) return rc;
+    }
     if (tile_px) {
         uint64_t total = (uint64_t)ctx->T * ctx->ts * ctx->ts;
         uint64_t blocks = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
@@ -353,149 +359,186 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
 // ---------------------------------------------------------------------------------------
 // wide vectors (N = 25 ... 16384, --mode 5 ... 128): tiled all-pairs kernel
 // ---------------------------------------------------------------------------------------
-// Query vectors do not fit in registers, so this is the classic shared-memory tiling: a CTA owns 64
-// queries, walks candidate tiles of 64, and for every (64 x 64) tile streams the vectors through shared
-// memory in slices of 32 words; each thread accumulates a 4 x 4 block of distances with VABSDIFF4.ACC
-// (2 LDS.128 per 16 VABSDIFF4).  Slices are stored word-major with an XOR swizzle so both the transposing
-// stores and the 128-bit reads are bank-conflict free.  The argmin keeps the canonical order (candidates are
-// visited in increasing rank, strict `<`).
-static constexpr int WQ = 64, WC = 64, WK = 32;
+// Query vectors do not fit in registers, so this is a shared-memory tiling fed by TMA.  Both operands are
+// stored pre-tiled and word-major in HBM:
+//     candidates [c-tile of 128][slice of 8 words][word][candidate]     (built once in emo_set_library)
+//     queries    [q-tile of 64 ][slice of 8 words][word][query]         (pack_queries_kernel, per call)
+// so one slice of a tile is a contiguous 4 KB / 2 KB block: a producer warp streams (query slice, candidate
+// slice) pairs through an 8-stage mbarrier ring with two cp.async.bulk copies per stage and nothing is
+// transposed or swizzled on the SM.  Warp w owns queries 8w..8w+7 (two warp-uniform LDS.128 per word), lane l
+// owns candidates 4l..4l+3 (one conflict-free LDS.128 per word): 3 LDS.128 feed 32 VABSDIFF4.ACC.
+// Candidates are visited in increasing rank and compared with strict `<`, lanes merge with a lexicographic
+// (dist, rank) shuffle minimum, splits with the 64-bit atomicMin: the canonical tie-break again.
+static constexpr int WQ = 64, WC = 128;  // slice depth WK (words) = 8, 16 or 32: the largest that divides the padded vector
 
+// dst layout [tile][slice][k][row_in_tile]; src bytes gathered per word
 __global__ void pack_queries_kernel(const uint8_t *__restrict__ src, uint32_t W, uint32_t bw, uint32_t Q, uint32_t Qpad,
-                                    uint32_t dim, uint32_t words, uint32_t *__restrict__ qvec) {
+                                    uint32_t dim, uint32_t words, uint32_t WK, uint32_t *__restrict__ qvec) {
     const uint64_t total = (uint64_t)Qpad * words;
-    const uint32_t D = 3 * dim * dim;
+    const uint32_t D = 3 * dim * dim, n_slices = words / WK;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t qi = (uint32_t)(i / words);
-        const uint32_t w = (uint32_t)(i % words);
+        const uint32_t row = (uint32_t)(i % WQ);
+        const uint32_t k = (uint32_t)((i / WQ) % WK);
+        const uint32_t sl = (uint32_t)((i / (WQ * WK)) % n_slices);
+        const uint32_t tile = (uint32_t)(i / ((uint64_t)WQ * WK * n_slices));
+        uint32_t qi = tile * WQ + row;
         if (qi >= Q) qi = Q - 1;
+        const uint32_t w = sl * WK + k;
         const uint32_t by = qi / bw, bx = qi % bw;
         uint32_t packed = 0;
-        for (uint32_t k = 0; k < 4; k++) {
-            const uint32_t b = w * 4 + k;
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t b = w * 4 + j;
             if (b < D) {
                 const uint32_t cell = b / 3, ch = b % 3, cy = cell / dim, cx = cell % dim;  // analysis.rs:23-36
-                packed |= (uint32_t)src[((size_t)(by * dim + cy) * W + (bx * dim + cx)) * 3 + ch] << (8 * k);
+                packed |= (uint32_t)src[((size_t)(by * dim + cy) * W + (bx * dim + cx)) * 3 + ch] << (8 * j);
             }
         }
         qvec[i] = packed;
     }
 }
 
-__global__ void __launch_bounds__(256) match_wide_kernel(const uint32_t *__restrict__ qvec, const uint32_t *__restrict__ cand,
-                                                         uint32_t words, uint32_t n_ctiles, uint32_t tiles_per_split, uint32_t Q,
-                                                         unsigned long long *__restrict__ keys) {
-    // double-buffered slices: the global loads of slice i+1 are in flight while slice i is consumed
-    __shared__ __align__(16) uint32_t sq[2][WK][WQ];
-    __shared__ __align__(16) uint32_t sc[2][WK][WC];
-    const int tid = threadIdx.x, tq = tid >> 4, tc = tid & 15;
-    const uint32_t q0 = blockIdx.x * WQ;
-    const uint32_t t0 = blockIdx.y * tiles_per_split, t1 = min(t0 + tiles_per_split, n_ctiles);
-    uint32_t bestd[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, besti[4] = {0, 0, 0, 0};
-    // loader mapping: thread -> (row = tid / 8 (+32), quad = tid % 8): 4 consecutive words of one vector
-    const int lrow = tid >> 3, lquad = tid & 7;
-    const uint32_t n_slices = (words + WK - 1) / WK;          // words is a multiple of 8; the last slice may be short
-    const uint32_t n_steps = (t1 - t0) * n_slices;
-    uint4 vq[2], vc[2];
-    auto fetch = [&](uint32_t step) {
-        const uint32_t t = t0 + step / n_slices, k = (step % n_slices) * WK + lquad * 4;
+// plain [Lpad][words] candidates -> [c-tile][slice][k][candidate]
+__global__ void tile_candidates_kernel(const uint32_t *__restrict__ plain, uint32_t Lpad, uint32_t words, uint32_t WK,
+                                       uint32_t *__restrict__ tiled) {
+    const uint64_t total = (uint64_t)Lpad * words;
+    const uint32_t n_slices = words / WK;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(i % WC);
+        const uint32_t k = (uint32_t)((i / WC) % WK);
+        const uint32_t sl = (uint32_t)((i / (WC * WK)) % n_slices);
+        const uint32_t tile = (uint32_t)(i / ((uint64_t)WC * WK * n_slices));
+        tiled[i] = plain[(size_t)(tile * WC + row) * words + sl * WK + k];
+    }
+}
+
+template <int WK>
+__global__ void __launch_bounds__(288, 2) match_wide_kernel(const uint32_t *__restrict__ qvec, const uint32_t *__restrict__ cand,
+                                                            uint32_t n_slices, uint32_t n_ctiles, uint32_t tiles_per_split,
+                                                            uint32_t Q, unsigned long long *__restrict__ keys) {
+    constexpr int WIDE_STAGES = 64 / WK;                     // 8 / 4 / 2 stages of 6 / 12 / 24 KB
+    constexpr int WIDE_STAGE_WORDS = WK * (WQ + WC);
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)WIDE_STAGES * WIDE_STAGE_WORDS * 4);
+    uint64_t *empty = full + WIDE_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int row = lrow + 32 * h;
-            if (k < words) {
-                vq[h] = __ldg(reinterpret_cast<const uint4 *>(qvec + (size_t)(q0 + row) * words + k));
-                vc[h] = __ldg(reinterpret_cast<const uint4 *>(cand + ((size_t)t * WC + row) * words + k));
-            } else {
-                vq[h] = make_uint4(0, 0, 0, 0);
-                vc[h] = make_uint4(0, 0, 0, 0);
-            }
+        for (int s = 0; s < WIDE_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
         }
-    };
-    auto stash = [&](int buf) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int col = (lrow + 32 * h) ^ (lquad << 2);  // swizzle: word rows 4*lquad..+3 share this column permutation
-            sq[buf][lquad * 4 + 0][col] = vq[h].x; sq[buf][lquad * 4 + 1][col] = vq[h].y;
-            sq[buf][lquad * 4 + 2][col] = vq[h].z; sq[buf][lquad * 4 + 3][col] = vq[h].w;
-            sc[buf][lquad * 4 + 0][col] = vc[h].x; sc[buf][lquad * 4 + 1][col] = vc[h].y;
-            sc[buf][lquad * 4 + 2][col] = vc[h].z; sc[buf][lquad * 4 + 3][col] = vc[h].w;
-        }
-    };
-    uint32_t acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0;
-    if (n_steps) {
-        fetch(0);
-        stash(0);
+        mbar_fence_init();
     }
     __syncthreads();
-    for (uint32_t step = 0; step < n_steps; step++) {
-        const int buf = step & 1;
-        if (step + 1 < n_steps) fetch(step + 1);
-        const uint32_t sl = step % n_slices;
-        const int kmax = (int)min((uint32_t)WK, words - sl * WK);
-#pragma unroll 8
-        for (int k = 0; k < kmax; k++) {
-            const int sw = (k >> 2) & 7;
-            const uint4 a4 = *reinterpret_cast<const uint4 *>(&sq[buf][k][(tq ^ sw) * 4]);
-            const uint4 c4 = *reinterpret_cast<const uint4 *>(&sc[buf][k][(tc ^ sw) * 4]);
-            const uint32_t qa[4] = {a4.x, a4.y, a4.z, a4.w}, cb[4] = {c4.x, c4.y, c4.z, c4.w};
+    const uint32_t t0 = blockIdx.y * tiles_per_split, t1 = min(t0 + tiles_per_split, n_ctiles);
+    const uint32_t n_steps = (t1 - t0) * n_slices;
+    if (warp == 8) {  // producer: one lane, two bulk copies per stage
+        if (lane == 0) {
+            const uint32_t *qbase = qvec + (size_t)blockIdx.x * n_slices * (WK * WQ);
+            for (uint32_t n = 0; n < n_steps; n++) {
+                const int s = n % WIDE_STAGES;
+                const uint32_t t = t0 + n / n_slices, sl = n % n_slices;
+                if (n >= WIDE_STAGES) mbar_wait_relaxed(&empty[s], ((n / WIDE_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&full[s], WIDE_STAGE_WORDS * 4);
+                uint32_t *dst = ring + (size_t)s * WIDE_STAGE_WORDS;
+                bulk_g2s(dst, qbase + (size_t)sl * (WK * WQ), WK * WQ * 4, &full[s]);
+                bulk_g2s(dst + WK * WQ, cand + ((size_t)t * n_slices + sl) * (WK * WC), WK * WC * 4, &full[s]);
+            }
+        }
+        return;
+    }
+    uint32_t acc[8][4], bestd[8], besti[8];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 8; a++) {
+        bestd[a] = 0xffffffffu;
+        besti[a] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0;
+    }
+    for (uint32_t n = 0; n < n_steps; n++) {
+        const int s = n % WIDE_STAGES;
+        mbar_wait(&full[s], (n / WIDE_STAGES) & 1);
+        const uint32_t *sq = ring + (size_t)s * WIDE_STAGE_WORDS + warp * 8;
+        const uint32_t *sc = ring + (size_t)s * WIDE_STAGE_WORDS + WK * WQ + lane * 4;
+#pragma unroll
+        for (int k = 0; k < WK; k++) {
+            const uint4 a0 = *reinterpret_cast<const uint4 *>(sq + k * WQ);
+            const uint4 a1 = *reinterpret_cast<const uint4 *>(sq + k * WQ + 4);
+            const uint4 c4 = *reinterpret_cast<const uint4 *>(sc + k * WC);
+            const uint32_t qa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, cb[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int a = 0; a < 8; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) acc[a][b] = sad4(qa[a], cb[b], acc[a][b]);
         }
-        if (sl == n_slices - 1) {  // tile finished: fold, candidates in increasing rank, strict `<`
-            const uint32_t t = t0 + step / n_slices;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (n % n_slices == n_slices - 1) {  // tile finished: fold (increasing rank, strict `<`)
+            const uint32_t cbase = (t0 + n / n_slices) * WC + lane * 4;
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int a = 0; a < 8; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    if (acc[a][b] < bestd[a]) { bestd[a] = acc[a][b]; besti[a] = t * WC + tc * 4 + b; }
+                    if (acc[a][b] < bestd[a]) { bestd[a] = acc[a][b]; besti[a] = cbase + b; }
                     acc[a][b] = 0;
                 }
         }
-        if (step + 1 < n_steps) stash(buf ^ 1);
-        __syncthreads();
     }
-    // merge the 16 lanes that share a query group (lexicographic (dist, rank) minimum), then across splits
+    // merge the 32 lanes (lexicographic (dist, rank) minimum), then across splits
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
+    for (int a = 0; a < 8; a++) {
         unsigned long long key = ((unsigned long long)bestd[a] << 32) | besti[a];
 #pragma unroll
-        for (int m = 1; m < 16; m <<= 1) {
+        for (int m = 1; m < 32; m <<= 1) {
             const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
             key = o < key ? o : key;
         }
-        const uint32_t qi = q0 + tq * 4 + a;
-        if (tc == 0 && qi < Q) atomicMin(&keys[qi], key);
+        const uint32_t qi = blockIdx.x * WQ + warp * 8 + a;
+        if (lane == 0 && qi < Q && n_steps) atomicMin(&keys[qi], key);
     }
+}
+
+static uint32_t wide_slice_words(uint32_t words) { return words % 32 == 0 ? 32 : (words % 16 == 0 ? 16 : 8); }
+
+int emo_launch_tile_candidates(emo_ctx *ctx) {  // called by emo_launch_build_library for wide libraries
+    const uint32_t Lpad = ctx->n_chunks * ctx->chunk;
+    int rc = emo_ensure(ctx, (void **)&ctx->qvec, &ctx->qvec_cap, (size_t)Lpad * ctx->words * 4);  // scratch for the plain layout
+    if (rc) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->qvec, ctx->cand, (size_t)Lpad * ctx->words * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    const uint64_t total = (uint64_t)Lpad * ctx->words, blocks = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 32;
+    tile_candidates_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(ctx->qvec, Lpad, ctx->words,
+                                                                                             wide_slice_words(ctx->words), ctx->cand);
+    EMO_LAUNCH_CHECK(ctx);
+    return EMO_OK;
 }
 
 static int launch_match_wide(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
     const uint32_t dim = ctx->dim, bw = W / dim, Q = bw * (H / dim), words = ctx->words;
+    const uint32_t WK = wide_slice_words(words), n_slices = words / WK;
     const uint32_t Qpad = (Q + WQ - 1) / WQ * WQ;
     int rc = emo_ensure(ctx, (void **)&ctx->qvec, &ctx->qvec_cap, (size_t)Qpad * words * 4);
     if (rc) return rc;
     if ((rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, (size_t)Q * 8))) return rc;
     {
         const uint64_t total = (uint64_t)Qpad * words, blocks = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 32;
-        pack_queries_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(src, W, bw, Q, Qpad, dim, words, ctx->qvec);
+        pack_queries_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(src, W, bw, Q, Qpad, dim, words, WK, ctx->qvec);
         EMO_LAUNCH_CHECK(ctx);
     }
     match_init_keys_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q);
     EMO_LAUNCH_CHECK(ctx);
+    const size_t smem = (size_t)64 * (WQ + WC) * 4 + 2 * 8 * 8;  // stages * WK = 64 words deep in every variant
+    auto kern = WK == 32 ? match_wide_kernel<32> : (WK == 16 ? match_wide_kernel<16> : match_wide_kernel<8>);
+    EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t qtiles = Qpad / WQ, n_ctiles = ctx->n_chunks;
     uint32_t splits = 1;
-    const uint32_t want = (uint32_t)ctx->sm_count * 8;
+    const uint32_t want = (uint32_t)ctx->sm_count * 6;  // 2 CTAs per SM, >= 3 waves
     if (qtiles < want) splits = (want + qtiles - 1) / qtiles;
     if (splits > n_ctiles) splits = n_ctiles;
     if (splits > 65535) splits = 65535;
     const uint32_t tps = (n_ctiles + splits - 1) / splits;
     splits = (n_ctiles + tps - 1) / tps;
-    match_wide_kernel<<<dim3(qtiles, splits), 256, 0, ctx->stream>>>(ctx->qvec, ctx->cand, words, n_ctiles, tps, Q, ctx->keys);
+    kern<<<dim3(qtiles, splits), 288, smem, ctx->stream>>>(ctx->qvec, ctx->cand, n_slices, n_ctiles, tps, Q, ctx->keys);
     EMO_LAUNCH_CHECK(ctx);
     match_finalize_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, 1u, item, dist);
     EMO_LAUNCH_CHECK(ctx);
