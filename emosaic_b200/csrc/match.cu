@@ -33,7 +33,7 @@
 
 static constexpr int MATCH_STAGES = 4;
 static constexpr int MATCH_WIN = 128;  // candidates between two argmin checks
-static constexpr int MATCH_UNROLL = 4;
+static constexpr int MATCH_UNROLL = 8;
 
 
 // ---------------------------------------------------------------------------------------
