@@ -303,9 +303,9 @@ def run_ours(args):
             "kernel": "match_kernel<1,8,256>", "bound": "int32-pipe",
             "achieved": achieved / 1e12, "peak": imad / 1e12, "unit": "Tint-op/s", "frac": achieved / imad,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload at N=1, from the committed
-            # ncu --set full capture profiles/r01c_ncu_full_match_kernel.txt (56.6 MB + 86.4 MB); algorithmic
+            # ncu --set full capture profiles/r01e_ncu_full_match_kernel.txt (55.1 MB + 81.2 MB); algorithmic
             # bytes are 50 MB source + 0.4 MB candidates in, 134 MB item/dist out
-            "traffic": 143006720 if world == 1 else None,
+            "traffic": 136288512 if world == 1 else None,
             "note": "achieved = 2*D*Q*L algorithmic integer ops / CUDA-event time of the match launch (avg over the timed "
                     "steps, rank 0); peak = scalar INT32 (IMAD) issue rate measured by emo_probe_int_pipe in this run; "
                     "frac > 1 is legitimate because one VABSDIFF4.U8.ACC performs 4 abs-diffs + 3 adds",
