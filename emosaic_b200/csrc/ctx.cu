@@ -365,6 +365,7 @@ int emo_match_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int3
     int rc = check_match_args(ctx, src, W, H);
     if (rc) return rc;
     EMO_REQUIRE(item && dist, EMO_ERR_ARG, "match: item/dist is NULL");
+    EMO_REQUIRE((uintptr_t)item % 4 == 0 && (uintptr_t)dist % 4 == 0, EMO_ERR_ARG, "match: item/dist must be 4-byte aligned");
     EMO_CK(cudaSetDevice(ctx->device));
     return emo_launch_match(ctx, src, W, H, item, dist);
 }
@@ -403,6 +404,8 @@ int emo_compose_dev(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint3
                     uint8_t tint_alpha, uint8_t *out) {
     int rc = check_compose_args(ctx, item, src, W, H, oc, out);
     if (rc) return rc;
+    EMO_REQUIRE((uintptr_t)item % 4 == 0, EMO_ERR_ARG, "compose: item map must be 4-byte aligned");
+    EMO_REQUIRE(oc == 3 || (uintptr_t)out % 4 == 0, EMO_ERR_ARG, "compose: RGBA output must be 4-byte aligned");
     EMO_CK(cudaSetDevice(ctx->device));
     return emo_launch_compose(ctx, item, src, W, H, oc, tint_alpha, out);
 }

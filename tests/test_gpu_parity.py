@@ -490,3 +490,38 @@ def test_random_geometry_sweep(ctx):
         rgb = oracle.render(tiles, ri)
         assert (out == oracle.tint(rgb, src, A)).all(), tag
         assert (ctx.compose(item) == rgb).all(), tag
+
+
+def test_unaligned_device_pointers(ctx):
+    """Device pointers with odd alignment take the generic kernels (or are rejected where a 4-byte store is needed)."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(77)
+    T, ts, bh, bw = 90, 16, 3, 32
+    tiles_h = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    src_h = rng.integers(0, 256, (bh, bw, 3), dtype=np.uint8)
+    raw = torch.zeros(T * ts * ts * 3 + 64, dtype=torch.uint8, device=dev)
+    raw[1:1 + T * ts * ts * 3] = torch.from_numpy(tiles_h.reshape(-1)).to(dev)     # tiles at an odd address
+    colors = torch.empty(T * 3 + 8, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    ctx.analyse_dev(raw.data_ptr() + 1, T, ts, 1, colors.data_ptr() + 1)
+    ctx.sync()
+    ch = colors[1:1 + T * 3].cpu().numpy().reshape(T, 1, 3)
+    assert (ch == oracle.analyse_tiles(tiles_h, 1)).all()
+    ctx.set_library(ch, tiles_h)
+    item_h, _ = oracle.match(ch, src_h)
+    item = torch.from_numpy(item_h.reshape(-1)).to(dev)
+    src = torch.from_numpy(src_h.reshape(-1)).to(dev)
+    out = torch.zeros(bh * ts * bw * ts * 4 + 64, dtype=torch.uint8, device=dev)
+    ctx.compose_dev(item.data_ptr(), 0, bw, bh, 3, 0, out.data_ptr() + 3)            # RGB out at an odd address
+    ctx.sync()
+    got = out[3:3 + bh * ts * bw * ts * 3].cpu().numpy().reshape(bh * ts, bw * ts, 3)
+    assert (got == oracle.render(tiles_h, item_h)).all()
+    ctx.compose_dev(item.data_ptr(), src.data_ptr(), bw, bh, 4, 127, out.data_ptr() + 4)   # 4-byte aligned RGBA: generic path
+    ctx.sync()
+    got4 = out[4:4 + bh * ts * bw * ts * 4].cpu().numpy().reshape(bh * ts, bw * ts, 4)
+    assert (got4 == oracle.tint(oracle.render(tiles_h, item_h), src_h, 127)).all()
+    with pytest.raises(emo.EmosaicError, match="4-byte aligned"):
+        ctx.compose_dev(item.data_ptr(), src.data_ptr(), bw, bh, 4, 127, out.data_ptr() + 2)
+    with pytest.raises(emo.EmosaicError, match="4-byte aligned"):
+        ctx.match_dev(src.data_ptr(), bw, bh, out.data_ptr() + 1, out.data_ptr() + 8)
