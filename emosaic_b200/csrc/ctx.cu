@@ -243,20 +243,53 @@ int emo_analyse_fused_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32
     return emo_launch_analyse_fused(ctx, tiles, T, ts, out1, out4);
 }
 
+// Host-pointer analysis streams the library through two device slabs (~256 MB each): the H2D of slab k+1 runs
+// on the copy stream while slab k is reduced, so a library larger than HBM (or than the caller wants to stage) works
+// and the kernels hide behind PCIe.  dim2 == 0: single analysis into out1; otherwise the fused 1to1 + 4to1 pass.
+static int analyse_host(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out1, uint8_t *out4,
+                        bool fused) {
+    const size_t tile_b = (size_t)ts * ts * 3;
+    const size_t out_per_tile = fused ? 15 : (size_t)dim * dim * 3;
+    uint64_t slab_tiles = (256ull << 20) / tile_b;
+    if (slab_tiles < 1) slab_tiles = 1;
+    if (slab_tiles > T) slab_tiles = T;
+    int rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], 2 * slab_tiles * tile_b))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], 2 * slab_tiles * out_per_tile))) return rc;
+    uint8_t *din[2] = {(uint8_t *)ctx->stage[0], (uint8_t *)ctx->stage[0] + slab_tiles * tile_b};
+    uint8_t *dout[2] = {(uint8_t *)ctx->stage[1], (uint8_t *)ctx->stage[1] + slab_tiles * out_per_tile};
+    uint32_t k = 0;
+    for (uint64_t t0 = 0; t0 < T; t0 += slab_tiles, k++) {
+        const uint64_t n = T - t0 < slab_tiles ? T - t0 : slab_tiles;
+        const int b = k & 1;
+        // slab buffer b is free once the kernel + D2H of slab k-2 (issued on the compute stream) are done
+        if (k >= 2) EMO_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[2 + b], 0));
+        EMO_CK(cudaMemcpyAsync(din[b], tiles + t0 * tile_b, n * tile_b, cudaMemcpyHostToDevice, ctx->copy_stream));
+        EMO_CK(cudaEventRecord(ctx->ev_pipe[b], ctx->copy_stream));
+        EMO_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[b], 0));
+        if (fused) {
+            uint8_t *d1 = dout[b], *d4 = dout[b] + n * 3;
+            if ((rc = emo_launch_analyse_fused(ctx, din[b], n, ts, d1, d4))) return rc;
+            EMO_CK(cudaMemcpyAsync(out1 + t0 * 3, d1, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+            EMO_CK(cudaMemcpyAsync(out4 + t0 * 12, d4, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            if ((rc = emo_launch_analyse(ctx, din[b], n, ts, dim, dout[b]))) return rc;
+            EMO_CK(cudaMemcpyAsync(out1 + t0 * out_per_tile, dout[b], n * out_per_tile, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        EMO_CK(cudaEventRecord(ctx->ev_pipe[2 + b], ctx->stream));
+    }
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->copy_stream));
+    return EMO_OK;
+}
+
 int emo_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse: ctx is NULL");
     int rc = check_analyse_args(tiles, T, ts, dim, out);
     if (rc) return rc;
     if (T == 0) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
-    size_t in_b = (size_t)T * ts * ts * 3, out_b = (size_t)T * dim * dim * 3;
-    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], in_b))) return rc;
-    if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], out_b))) return rc;
-    EMO_CK(cudaMemcpyAsync(ctx->stage[0], tiles, in_b, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = emo_launch_analyse(ctx, (const uint8_t *)ctx->stage[0], T, ts, dim, (uint8_t *)ctx->stage[1]))) return rc;
-    EMO_CK(cudaMemcpyAsync(out, ctx->stage[1], out_b, cudaMemcpyDeviceToHost, ctx->stream));
-    EMO_CK(cudaStreamSynchronize(ctx->stream));
-    return EMO_OK;
+    return analyse_host(ctx, tiles, T, ts, dim, out, nullptr, false);
 }
 
 int emo_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
@@ -267,16 +300,7 @@ int emo_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t t
     EMO_REQUIRE(ts % 2 == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by 2");
     if (T == 0) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
-    size_t in_b = (size_t)T * ts * ts * 3;
-    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], in_b))) return rc;
-    if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], (size_t)T * 15))) return rc;
-    uint8_t *d1 = (uint8_t *)ctx->stage[1], *d4 = d1 + (size_t)T * 3;
-    EMO_CK(cudaMemcpyAsync(ctx->stage[0], tiles, in_b, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = emo_launch_analyse_fused(ctx, (const uint8_t *)ctx->stage[0], T, ts, d1, d4))) return rc;
-    EMO_CK(cudaMemcpyAsync(out1, d1, (size_t)T * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    EMO_CK(cudaMemcpyAsync(out4, d4, (size_t)T * 12, cudaMemcpyDeviceToHost, ctx->stream));
-    EMO_CK(cudaStreamSynchronize(ctx->stream));
-    return EMO_OK;
+    return analyse_host(ctx, tiles, T, ts, 2, out1, out4, true);
 }
 
 static int check_library_args(const void *colors, uint32_t T, uint32_t N, uint32_t ts, const void *px) {
