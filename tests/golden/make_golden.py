@@ -69,3 +69,12 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "ties_palette.npz"), N=1, tiles=tiles, src=src, colors=colors, item=item,
                         dist=dist, out_sha256=sha(oracle.render(tiles, item)))
     print("ties_palette", int(dist.max()), np.unique(item).size)
+    # .emosaic_4to1 bytes (bincode 1.3.3 defaults) for 5 tiles: dates on tiles 1 and 3, one non-ASCII path
+    rng = np.random.default_rng(7)
+    ccol = rng.integers(0, 256, (5, 4, 3), dtype=np.uint8)
+    cpaths = ["/photos/a.jpg", "/photos/sub dir/b.jpeg", "/photos/c.jpg", "/photos/déjà.jpg", "rel/e.jpg"]
+    cdates = [None, "2021:06:01", None, "2019:12:31", None]
+    blob = oracle.cache_serialize(ccol, np.arange(1, 6), cdates, cpaths)
+    open(os.path.join(HERE, "cache_4to1.bin"), "wb").write(blob)
+    np.savez_compressed(os.path.join(HERE, "cache_4to1_meta.npz"), colors=ccol, paths=np.array(cpaths), dates=np.array([d or "" for d in cdates]))
+    print("cache_4to1.bin", len(blob), "bytes")

@@ -151,3 +151,19 @@ def test_cli_parser_accepts_both_spellings():
     assert cli.MODES[a.mode] == 2 and a.force and a.tint_opacity == 0.5 and a.tile_size == 8
     a = p.parse_args(["img.png", "mosaic", "tiles", "--mode", "128"])
     assert cli.MODES[a.mode] == 128 and a.tile_size == 16 and a.output_path == "./output.jpg"
+
+
+def test_cache_golden_bytes():
+    """A committed .emosaic_4to1 blob: the Python serialiser reproduces it byte for byte and the loader reads it back."""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    blob = open(os.path.join(here, "cache_4to1.bin"), "rb").read()
+    meta = np.load(os.path.join(here, "cache_4to1_meta.npz"))
+    paths = [str(p) for p in meta["paths"]]
+    dates = [str(d) or None for d in meta["dates"]]
+    assert emo.serialize_tile_set(meta["colors"], paths, dates) == blob
+    c, p, d = emo.deserialize_tile_set(blob, 4)
+    assert (c == meta["colors"]).all() and p == paths and d == dates
+    # hand-decoded header: 5 tiles, 12 colour bytes each
+    assert blob[:8] == (5).to_bytes(8, "little") and blob[8:16] == (12).to_bytes(8, "little")
+    assert len(blob) == 8 + 5 * (8 + 12 + 2 + 1) + 2 * (8 + 10) + 8 + sum(8 + len(x.encode()) for x in paths)
