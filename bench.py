@@ -141,6 +141,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU arm is meant to use all host threads
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     cfg = C4
     oracle, tiles, src, colors, kd, build_s = cpu_reference_setup(cfg)
     dt, px, _ = cpu_step(oracle, kd, tiles, src, 0, 8)
