@@ -137,6 +137,22 @@ def cpu_baseline(cfg, target_s=12.0):
             "seconds": dt}
 
 
+def cpu_baseline_spread(cfg, rows=64):
+    """Context for cpu_baseline: the same CPU code on a KD-tree-friendly library (tile colours uniform in the cube
+    instead of clustered at 127 +- 9, which is what averaging uniform-random tile pixels produces)."""
+    import oracle
+    rng = np.random.default_rng(4321)
+    colors = rng.integers(0, 256, (cfg["T"], 1, 3), dtype=np.uint8)
+    src = np.random.default_rng(5678).integers(0, 256, (rows, cfg["W"], 3), dtype=np.uint8)
+    kd = oracle.KdTree(colors)
+    kd.match(src[:8])
+    t0 = time.perf_counter()
+    kd.match(src)
+    dt = time.perf_counter() - t0
+    return {"value": rows * cfg["W"] / dt, "unit": "px/s", "cores": oracle.num_threads(),
+            "sample": f"{rows} source rows, match only, library colours uniform in the colour cube (KD-tree best case)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -329,6 +345,8 @@ def run_ours(args):
         if world == 1 and not args.no_extras:
             extra.update(extras(ctx, torch, dev, hbm_peak, peak_src))
         cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
+        if cpu is not None:
+            extra["cpu_baseline_spread_library"] = cpu_baseline_spread(cfg)
         line = {
             "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
