@@ -126,7 +126,7 @@ __device__ __forceinline__ uint32_t sad_vec(const uint32_t (&q)[WORDS], const ui
 }
 
 template <int WORDS, int R, int NT>
-__global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : (WORDS > 4 ? 3 : 6))) match_kernel(const MatchParams p) {
+__global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : (WORDS > 4 ? 3 : (R >= 4 ? 4 : 6)))) match_kernel(const MatchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage_words = p.chunk * WORDS;
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem);
@@ -562,10 +562,14 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
     p.dist = dist;
     p.keys = nullptr;
     const uint32_t Q = p.Q;
-    // R = 8 queries per thread amortises the candidate loads best but needs long scans and many queries to pay
-    // for its 2048-query CTAs; otherwise 256-query CTAs (R = 2) balance better (tools/sweep_match.py).
-    bool big = Q >= 65536u && ctx->L >= 32768u && ctx->words == 1;
-    if (const char *e = getenv("EMO_MATCH_R")) big = atoi(e) >= 8;  // tuning override
+    // Launch shape from tools/sweep_match.py (1to1): R = 8 queries per thread (2048-query CTAs) amortises the
+    // candidate loads best once the scan is long (L >= 16k) and there are enough queries; short libraries with many
+    // queries prefer R = 4 (512-query CTAs); everything else R = 2 (256-query CTAs) to keep the GPU busy.
+    int shape = 2;
+    if (ctx->words == 1 && Q >= 65536u) shape = ctx->L >= 16384u ? 8 : 4;
+    if (const char *e = getenv("EMO_MATCH_R")) shape = atoi(e);  // tuning override
+    if (ctx->words == 1 && shape == 4) return launch_match_t<1, 4, 128>(ctx, p, Q);
+    const bool big = shape >= 8;
     switch (ctx->words) {
         case 1: return big ? launch_match_t<1, 8, 256>(ctx, p, Q) : launch_match_t<1, 2, 128>(ctx, p, Q);
         case 3: return big ? launch_match_t<3, 8, 256>(ctx, p, Q) : launch_match_t<3, 2, 128>(ctx, p, Q);
