@@ -207,6 +207,16 @@ class Context:
         check(self._lib.emo_compose(self._h, _ptr(item), _ptr(src), W, H, out_channels, tint_alpha, _ptr(out)))
         return out
 
+    def compose_overlay(self, item, overlay, tint_alpha: int):
+        """Tint with an overlay image of any size (the original image of main.rs:447-478): RGBA result."""
+        item = np.ascontiguousarray(item, dtype=np.int32)
+        overlay = _u8(overlay)
+        bh, bw = item.shape
+        out = np.zeros((bh * self.ts, bw * self.ts, 4), np.uint8)
+        check(self._lib.emo_compose_overlay(self._h, _ptr(item), bw * self.dim, bh * self.dim, _ptr(overlay), overlay.shape[1],
+                                            overlay.shape[0], tint_alpha, _ptr(out)))
+        return out
+
     def compose_dev(self, item_dev: int, src_dev: int, W: int, H: int, out_channels: int, tint_alpha: int, out_dev: int):
         check(self._lib.emo_compose_dev(self._h, C.c_void_p(item_dev), C.c_void_p(src_dev or 0), W, H, out_channels,
                                         tint_alpha, C.c_void_p(out_dev)))

@@ -159,10 +159,13 @@ def main(argv=None) -> int:
         ctx.set_library(colors, px)
         out, item, dist = ctx.mosaic(img, 3, 0)
         stats.summarise(item, dist, paths)
-        src_for_tint = img
+        src_for_tint = original  # main.rs:447-466 overlays the image as opened, not the copy resized for matching
 
     if args.tint_opacity > 0.0:  # main.rs:447-478: RGBA PNG, early return (no stats image)
-        rgba = ctx.compose(item, src_for_tint, 4, api.tint_alpha(args.tint_opacity))
+        if src_for_tint.shape[0] == item.shape[0] * dim and src_for_tint.shape[1] == item.shape[1] * dim:
+            rgba = ctx.compose(item, src_for_tint, 4, api.tint_alpha(args.tint_opacity))
+        else:
+            rgba = ctx.compose_overlay(item, src_for_tint, api.tint_alpha(args.tint_opacity))
         Image.fromarray(rgba, "RGBA").save(args.output_path, format="PNG")
         return 0
     print(f"Writing output file to {args.output_path}", file=sys.stderr)

@@ -98,6 +98,8 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
 int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t W, uint32_t H,
                        uint32_t out_channels, uint8_t tint_alpha, uint8_t *out);
 int emo_prepare_tint(emo_ctx *ctx, uint8_t alpha);
+int emo_launch_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t H, const uint8_t *overlay, uint32_t ow,
+                               uint32_t oh, uint8_t tint_alpha, uint8_t *out);
 
 // ---------------------------------------------------------------------------------------
 // device helpers

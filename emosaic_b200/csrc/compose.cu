@@ -388,3 +388,20 @@ int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, ui
     EMO_LAUNCH_CHECK(ctx);
     return EMO_OK;
 }
+
+// Tint with an overlay image whose size differs from the matched source (src/main.rs:447-478 overlays the ORIGINAL
+// image, which n_to_1 may have resized before matching: --downsample > 1 or dimensions not divisible by dim).
+// Any ratio: the generic kernel samples floor((X + 0.5) * ow / OW) like image 0.25.2 resize(Nearest).
+int emo_launch_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t H, const uint8_t *overlay, uint32_t ow,
+                               uint32_t oh, uint8_t tint_alpha, uint8_t *out) {
+    const uint32_t ts = ctx->ts, dim = ctx->dim, bw = W / dim, bh = H / dim;
+    int rc = emo_prepare_tint(ctx, tint_alpha);
+    if (rc) return rc;
+    const emo_tint_tables &t = ctx->tint;
+    const uint64_t total = (uint64_t)bw * ts * bh * ts;
+    const uint64_t blocks = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 32;
+    compose_generic_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+        ctx->lib_px, item, ctx->T, ts, dim, bw, bh, overlay, ow, oh, 4, t.lut, t.alpha_out, out, ctx->err_flag);
+    EMO_LAUNCH_CHECK(ctx);
+    return EMO_OK;
+}

@@ -457,6 +457,37 @@ int emo_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t 
     return emo_check_device_flag(ctx);
 }
 
+int emo_compose_overlay_dev(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t H, const uint8_t *overlay, uint32_t ow,
+                            uint32_t oh, uint8_t tint_alpha, uint8_t *out) {
+    int rc = check_compose_args(ctx, item, overlay, W, H, 4, out);
+    if (rc) return rc;
+    EMO_REQUIRE(ow > 0 && oh > 0, EMO_ERR_ARG, "compose_overlay: empty overlay %ux%u", ow, oh);
+    EMO_REQUIRE((uintptr_t)item % 4 == 0 && (uintptr_t)out % 4 == 0, EMO_ERR_ARG, "compose_overlay: item/out must be 4-byte aligned");
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_compose_overlay(ctx, item, W, H, overlay, ow, oh, tint_alpha, out);
+}
+
+int emo_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t H, const uint8_t *overlay, uint32_t ow, uint32_t oh,
+                        uint8_t tint_alpha, uint8_t *out) {
+    int rc = check_compose_args(ctx, item, overlay, W, H, 4, out);
+    if (rc) return rc;
+    EMO_REQUIRE(ow > 0 && oh > 0, EMO_ERR_ARG, "compose_overlay: empty overlay %ux%u", ow, oh);
+    EMO_CK(cudaSetDevice(ctx->device));
+    const uint32_t bw = W / ctx->dim, bh = H / ctx->dim;
+    const size_t Q = (size_t)bw * bh, ob = Q * ctx->ts * ctx->ts * 4, sb = (size_t)ow * oh * 3;
+    if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], Q * 4))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[5], &ctx->stage_cap[5], ob))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], sb))) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[3], item, Q * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EMO_CK(cudaMemcpyAsync(ctx->stage[2], overlay, sb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = emo_launch_compose_overlay(ctx, (const int32_t *)ctx->stage[3], W, H, (const uint8_t *)ctx->stage[2], ow, oh, tint_alpha,
+                                         (uint8_t *)ctx->stage[5])))
+        return rc;
+    EMO_CK(cudaMemcpyAsync(out, ctx->stage[5], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return emo_check_device_flag(ctx);
+}
+
 // Whole path with host buffers: the source goes up once, then block-row chunks are matched and
 // composed on the compute stream while the previous chunk's output drains to the host on the
 // copy stream (two device output buffers).

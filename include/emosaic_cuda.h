@@ -129,6 +129,15 @@ int emo_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t 
 int emo_compose_dev(emo_ctx *ctx, const int32_t *item_dev, const uint8_t *src_dev, uint32_t W, uint32_t H,
                     uint32_t out_channels, uint8_t tint_alpha, uint8_t *out_dev);
 
+/* Tint with an overlay image of a different size than the matched source: src/main.rs:447-478 overlays the ORIGINAL
+ * image, which n_to_1 (main.rs:567-595) may have resized before matching (--downsample > 1, or dimensions that are not
+ * multiples of dim).  overlay [oh,ow,3]; (W, H) are the dimensions of the matched source that produced `item`;
+ * out [H/dim*ts, W/dim*ts, 4].  Sampling: floor((X + 0.5) * ow / OW) in f32, image 0.25.2 resize(Nearest). */
+int emo_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t H, const uint8_t *overlay, uint32_t ow,
+                        uint32_t oh, uint8_t tint_alpha, uint8_t *out);
+int emo_compose_overlay_dev(emo_ctx *ctx, const int32_t *item_dev, uint32_t W, uint32_t H, const uint8_t *overlay_dev,
+                            uint32_t ow, uint32_t oh, uint8_t tint_alpha, uint8_t *out_dev);
+
 /* ---- whole path, host buffers ------------------------------------------------------------
  * render_nto1 (+ tint) in one call: H2D(src) -> match -> compose -> D2H(out) with the copies
  * pipelined against the kernels in block-row chunks. item/dist may be NULL. */

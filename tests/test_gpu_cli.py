@@ -92,3 +92,23 @@ def test_cli_rejects(workdir):
     assert cli.main(base + ["--no-repeat"]) == 2
     assert cli.main(["-s", "9", str(d / "src.png"), "mosaic", str(d / "tiles"), "-m", "2"]) == 1  # tile size % dim
     assert cli.main(["-s", "8", str(d / "src.png"), "mosaic", str(d / "nope")]) == 1
+
+
+def test_cli_tint_uses_original_image_as_overlay(workdir):
+    """--downsample 2 with -t: matching runs on the resized source, the tint overlay is the image as opened
+    (main.rs:396-398 / :447-466), nearest-resized to the output."""
+    d, src = workdir
+    ts = 8
+    out = d / "tint_ds.png"
+    assert cli.main(["-s", str(ts), "-o", str(out), "--crop", str(d / "src.png"), "mosaic", str(d / "tiles"), "-t", "0.5",
+                     "--downsample", "2", "-f"]) == 0
+    from emosaic_b200 import api
+    nw, nh = api.adjust_source_dims(src.shape[1], src.shape[0], 2, 1)
+    small = np.asarray(PIL.fromarray(src).resize((nw, nh), PIL.LANCZOS), dtype=np.uint8)
+    paths = cli.find_images(str(d / "tiles"), {"jpg", "jpeg"})
+    px = np.stack([cli.prepare_tile(p, ts, True) for p in paths])
+    colors = oracle.analyse_tiles(px, 1)
+    item, _ = oracle.match(colors, small)
+    want = oracle.tint(oracle.render(px, item), src, 127)
+    got = np.asarray(PIL.open(out))
+    assert got.shape == (nh * ts, nw * ts, 4) and (got == want).all()

@@ -525,3 +525,21 @@ def test_unaligned_device_pointers(ctx):
         ctx.compose_dev(item.data_ptr(), src.data_ptr(), bw, bh, 4, 127, out.data_ptr() + 2)
     with pytest.raises(emo.EmosaicError, match="4-byte aligned"):
         ctx.match_dev(src.data_ptr(), bw, bh, out.data_ptr() + 1, out.data_ptr() + 8)
+
+
+@pytest.mark.parametrize("A", [0, 64, 127, 200, 255])
+def test_tint_overlay_of_another_size(ctx, A):
+    """main.rs:447-478 overlays the ORIGINAL image (any size) nearest-resized to the output: emo_compose_overlay."""
+    rng = np.random.default_rng(A + 5)
+    for N, ts, bh, bw, oh, ow in ((1, 8, 9, 13, 37, 50), (4, 16, 5, 6, 21, 25), (1, 5, 7, 4, 3, 2), (9, 12, 3, 4, 100, 90)):
+        dim = int(N ** 0.5)
+        T = 30
+        tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+        colors = oracle.analyse_tiles(tiles, N)
+        item = rng.integers(1, T + 1, (bh, bw)).astype(np.int32)
+        item[rng.random((bh, bw)) < 0.3] *= -1
+        overlay = rng.integers(0, 256, (oh, ow, 3), dtype=np.uint8)
+        ctx.set_library(colors, tiles)
+        got = ctx.compose_overlay(item, overlay, A)
+        want = oracle.tint(oracle.render(tiles, item), overlay, A)
+        assert (got == want).all(), (N, ts, bh, bw, oh, ow)
