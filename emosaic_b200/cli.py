@@ -88,6 +88,23 @@ def main(argv=None) -> int:
     args = build_parser().parse_args(argv)
     from PIL import Image
     ts = args.tile_size
+    # main.rs:270-345 validate_tile_size / validate_input_image / validate_output_path
+    if ts == 0:
+        print("error: Tile size must be greater than 0", file=sys.stderr)
+        return 1
+    if ts > 1024:
+        print("error: Tile size is too large (maximum: 1024)", file=sys.stderr)
+        return 1
+    if not os.path.isfile(args.img):
+        print(f"error: Input image does not exist: {args.img}", file=sys.stderr)
+        return 1
+    if os.path.splitext(args.img)[1][1:].lower() not in ("jpg", "jpeg", "png", "bmp", "gif", "tiff", "webp"):
+        print(f"error: Unsupported image format: {os.path.splitext(args.img)[1][1:]}", file=sys.stderr)
+        return 1
+    out_parent = os.path.dirname(args.output_path)
+    if out_parent and not os.path.isdir(out_parent):
+        print(f"error: Output directory does not exist: {out_parent}", file=sys.stderr)
+        return 1
     if args.subcmd == "prepare":
         Image.fromarray(prepare_tile(args.img, ts, args.crop)).save(args.output_path)
         return 0

@@ -92,6 +92,10 @@ def test_cli_rejects(workdir):
     assert cli.main(base + ["--no-repeat"]) == 2
     assert cli.main(["-s", "9", str(d / "src.png"), "mosaic", str(d / "tiles"), "-m", "2"]) == 1  # tile size % dim
     assert cli.main(["-s", "8", str(d / "src.png"), "mosaic", str(d / "nope")]) == 1
+    assert cli.main(["-s", "0", str(d / "src.png"), "mosaic", str(d / "tiles")]) == 1      # main.rs:272-283
+    assert cli.main(["-s", "2048", str(d / "src.png"), "mosaic", str(d / "tiles")]) == 1
+    assert cli.main(["-s", "8", str(d / "missing.png"), "mosaic", str(d / "tiles")]) == 1
+    assert cli.main(["-s", "8", "-o", str(d / "no_dir" / "o.png"), str(d / "src.png"), "mosaic", str(d / "tiles")]) == 1
 
 
 def test_cli_tint_uses_original_image_as_overlay(workdir):
