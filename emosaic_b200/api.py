@@ -41,6 +41,10 @@ def _isqrt_exact(N: int) -> int:
     return d
 
 
+MATCH_AUTO, MATCH_SCAN, MATCH_INDEX = 0, 1, 2
+MATCH_MODES = {"auto": MATCH_AUTO, "scan": MATCH_SCAN, "index": MATCH_INDEX}
+
+
 class Context:
     """One per GPU (one process per GPU under torchrun).  Wraps ``emo_ctx``."""
 
@@ -175,6 +179,17 @@ class Context:
     def set_library_dev(self, colors_dev: int, tile_px_dev: int, T: int, N: int, ts: int):
         check(self._lib.emo_set_library_dev(self._h, C.c_void_p(colors_dev), C.c_void_p(tile_px_dev or 0), T, N, ts))
         self.T, self.N, self.dim, self.ts = T, N, _isqrt_exact(N), ts
+
+    # -- (2b) search index ------------------------------------------------------------------
+    def build_index(self):
+        """1to1 only: exact nearest-tile table over the colour cube (the KD-tree's job, tileset.rs:178-190)."""
+        check(self._lib.emo_build_index(self._h))
+
+    def set_match_mode(self, mode: int | str):
+        """'auto' (default) | 'scan' (brute force) | 'index' (colour-cube table when the library supports one)."""
+        if isinstance(mode, str):
+            mode = MATCH_MODES[mode]
+        check(self._lib.emo_set_match_mode(self._h, int(mode)))
 
     # -- (3) match ------------------------------------------------------------------------
     def match(self, src):

@@ -76,6 +76,9 @@ struct emo_ctx {
     uint8_t *lib_px = nullptr; // [2T][ts][ts][3]: entry 2t = tile t, 2t+1 = tile t mirrored
     size_t lib_cap = 0;
     bool has_px = false;
+    uint32_t *lut = nullptr;  // 1to1 search index: [256 b][256 g][256 r] keys dist << 22 | tile (index.cu), 64 MiB
+    bool lut_valid = false;   // built for the resident library
+    int match_mode = 0;       // EMO_MATCH_AUTO / SCAN / INDEX
 
     // scratch
     unsigned long long *keys = nullptr;  // [Q] packed (dist<<32 | candidate) for split matching
@@ -95,6 +98,10 @@ int emo_launch_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t 
 int emo_launch_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4);
 int emo_launch_build_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px);
 int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);
+int emo_launch_build_index(emo_ctx *ctx);
+int emo_prepare_match(emo_ctx *ctx, uint64_t queries);  // builds the 1to1 index when the mode / size rule asks for it
+bool emo_index_supported(const emo_ctx *ctx);
+int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);
 int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, uint32_t W, uint32_t H,
                        uint32_t out_channels, uint8_t tint_alpha, uint8_t *out);
 int emo_prepare_tint(emo_ctx *ctx, uint8_t alpha);

@@ -62,6 +62,7 @@ void emo_destroy(emo_ctx *ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->cand);
     cudaFree(ctx->lib_px);
+    cudaFree(ctx->lut);
     cudaFree(ctx->keys);
     cudaFree(ctx->qvec);
     cudaFree(ctx->err_flag);
@@ -329,6 +330,7 @@ static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, boo
         return EMO_ERR_UNSUPPORTED;
     }
     ctx->T = T; ctx->N = N; ctx->dim = dim; ctx->ts = ts; ctx->words = words;
+    ctx->lut_valid = false;  // the search index belongs to the previous library
     ctx->L = (N == 1) ? T : 2 * T;  // for N == 1 a tile and its mirror coincide; the mirror can never win a tie
     uint32_t chunk = (words == 1) ? 1024 : (words == 3 ? 512 : 256);
     if (ctx->wide) chunk = 128;  // candidate tile of match_wide_kernel
@@ -370,6 +372,25 @@ int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px,
     if ((rc = emo_launch_build_library(ctx, (const uint8_t *)ctx->stage[0], tile_px ? (const uint8_t *)ctx->stage[1] : nullptr)))
         return rc;
     EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
+int emo_build_index(emo_ctx *ctx) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_build_index: ctx is NULL");
+    EMO_REQUIRE(ctx->T > 0, EMO_ERR_STATE, "emo_build_index: no library set (call emo_set_library first)");
+    if (!emo_index_supported(ctx)) {
+        emo_set_error("emo_build_index: the colour-cube index exists for N == 1 and T <= 2^22 (N=%u, T=%u)", ctx->N, ctx->T);
+        return EMO_ERR_UNSUPPORTED;
+    }
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_build_index(ctx);
+}
+
+int emo_set_match_mode(emo_ctx *ctx, int mode) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_match_mode: ctx is NULL");
+    EMO_REQUIRE(mode == EMO_MATCH_AUTO || mode == EMO_MATCH_SCAN || mode == EMO_MATCH_INDEX, EMO_ERR_ARG,
+                "emo_set_match_mode: unknown mode %d", mode);
+    ctx->match_mode = mode;
     return EMO_OK;
 }
 
@@ -520,6 +541,7 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
     uint32_t *ddist = (uint32_t *)ctx->stage[4];
     uint8_t *dout[2] = {(uint8_t *)ctx->stage[5], (uint8_t *)ctx->stage[5] + chunk_out};
     EMO_CK(cudaMemcpyAsync(dsrc, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = emo_prepare_match(ctx, Q))) return rc;  // decide on the 1to1 index for the whole image, not per chunk
     uint32_t k = 0;
     for (uint32_t r0 = 0; r0 < bh; r0 += rows_per_chunk, k++) {
         uint32_t nr = bh - r0 < rows_per_chunk ? bh - r0 : rows_per_chunk;

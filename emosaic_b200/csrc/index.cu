@@ -1,0 +1,198 @@
+// index.cu — the 1to1 search index: an exact L1 nearest-tile table over the 24-bit colour cube.
+//
+// Reference: TileSet::build_kiddo() src/mosaic/tiles/tileset.rs:178-190 builds a KD-tree over the
+// library once per render (rendering.rs:136) and every block then asks it for nearest_one::<Manhattan>
+// (rendering.rs:187-195).  For --mode 1 the query is one RGB pixel, so the whole query space has only
+// 2^24 points: this file builds the answer for all of them and turns the per-pixel search into one
+// 4-byte load.  The answers are the brute-force kernel's answers bit for bit (match.cu):
+// minimum L1 distance, ties to the smallest tile index (the mirrored twin of a 1x1 colour vector is
+// the vector itself and can never win, so every item is positive).
+//
+// Construction = exact city-block distance transform.  |dr|+|dg|+|db| separates per axis, so
+//     best(r,g,b) = min_b' ( |b-b'| + min_g' ( |g-g'| + min_r' ( |r-r'| + seed(r',g',b') ) ) )
+// where seed is 0 at library colours and +inf elsewhere.  Cells hold key = dist << 22 | tile, so an
+// unsigned min is the lexicographic (dist, tile) min the tie-break asks for and adding k << 22 moves
+// only the distance.  Each axis pass is the classic forward/backward sweep (key[i] = min(key[i],
+// key[i-1] + 1<<22)), exact for L1.  dist <= 765 < 2^10 and tile < 2^22; larger libraries keep using
+// the scan kernel.
+//
+// Layout in HBM: lut[b][g][r] u32 (cell = r | g << 8 | b << 16, i.e. the low 24 bits of the pixel
+// read as a little-endian word), 64 MiB, resident in the 126 MB L2 while the source streams through.
+// Cost: build = 1 memset + 4 small kernels (about 0.1 ms, once per library); lookup = 3 B read +
+// 8 B written per query plus one L2-resident gather.
+#include "common.cuh"
+
+static constexpr uint32_t IDX_TILE_BITS = 22;
+static constexpr uint32_t IDX_INC = 1u << IDX_TILE_BITS;
+static constexpr uint32_t IDX_TILE_MASK = IDX_INC - 1;
+static constexpr uint32_t IDX_EMPTY = 0xFFFFFFFFu;
+static constexpr size_t IDX_CELLS = (size_t)1 << 24;
+
+// key + k steps, keeping "no tile yet" as it is (a real key never wraps: dist <= 765, k <= 255)
+__device__ __forceinline__ uint32_t idx_step(uint32_t key, uint32_t k) {
+    const uint32_t n = key + k * IDX_INC;
+    return n < key ? IDX_EMPTY : n;
+}
+
+// seeds: lut[colour of tile t] = min(t) — duplicates of a colour keep the smallest tile index
+__global__ void index_seed_kernel(const uint32_t *__restrict__ cand, uint32_t T, uint32_t *__restrict__ lut) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) atomicMin(&lut[cand[t] & 0xFFFFFFu], t);
+}
+
+// Pass along r (the contiguous axis): one warp per 256-cell line, 8 consecutive cells per lane (two
+// LDG.128 / STG.128), prefix- and suffix-min across lanes by shuffle.  Offsetting a lane's boundary
+// key by its distance to the far end of the line turns "min of key + distance" into a plain min-scan.
+__global__ void __launch_bounds__(256) index_sweep_r_kernel(uint32_t *__restrict__ lut) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // g | b << 8
+    uint4 *p = reinterpret_cast<uint4 *>(lut + ((size_t)line << 8)) + lane * 2;
+    const uint4 a = p[0], b = p[1];
+    uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t f[8], s[8];
+    // inside the lane
+    f[0] = k[0];
+#pragma unroll
+    for (int m = 1; m < 8; m++) f[m] = min(k[m], idx_step(f[m - 1], 1));
+    s[7] = k[7];
+#pragma unroll
+    for (int m = 6; m >= 0; m--) s[m] = min(k[m], idx_step(s[m + 1], 1));
+    // across lanes: forward carries leave from cell 7 of a lane, backward carries from cell 0
+    uint32_t uf = idx_step(f[7], (31 - lane) * 8);  // distance to the line's last lane, in lanes * 8
+    uint32_t ub = idx_step(s[0], lane * 8);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t of = __shfl_up_sync(0xFFFFFFFFu, uf, d), ob = __shfl_down_sync(0xFFFFFFFFu, ub, d);
+        if (lane >= (uint32_t)d) uf = min(uf, of);
+        if (lane + d < 32) ub = min(ub, ob);
+    }
+    uint32_t ef = __shfl_up_sync(0xFFFFFFFFu, uf, 1), eb = __shfl_down_sync(0xFFFFFFFFu, ub, 1);
+    if (lane == 0) ef = IDX_EMPTY;
+    if (lane == 31) eb = IDX_EMPTY;
+    // carry at my cell 0 (forward) / cell 7 (backward): remove the offset, the lane boundary is 1 cell away
+    // ef = key + (8 * (lane - l') + (31 - lane) * 8) steps seen from cell 7 of lane l'; cell 0 of mine is 8 * (lane - l') - 7 away
+    const uint32_t cf = ef == IDX_EMPTY ? IDX_EMPTY : ef - ((31 - lane) * 8 + 7) * IDX_INC;
+    const uint32_t cb = eb == IDX_EMPTY ? IDX_EMPTY : eb - (lane * 8 + 7) * IDX_INC;
+    uint32_t o[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) o[m] = min(min(f[m], s[m]), min(idx_step(cf, m), idx_step(cb, 7 - m)));
+    p[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    p[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// Pass along g (stride 256 cells) or b (stride 65 536 cells): one thread per line, neighbouring threads on
+// neighbouring r so every access of a warp is one 128-byte row.  Forward sweep in place, then the backward
+// sweep over the forward result (min(F, B) in one go).  Loads do not depend on the running minimum, so they
+// are issued 8 deep.
+template <int AXIS>  // 1: g, 2: b
+__global__ void __launch_bounds__(256) index_sweep_kernel(uint32_t *__restrict__ lut) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;  // 65 536 lines
+    const uint32_t r = id & 255, o = id >> 8;
+    const size_t base = AXIS == 1 ? ((size_t)o << 16 | r) : ((size_t)o << 8 | r);
+    const size_t stride = AXIS == 1 ? 256 : 65536;
+    uint32_t *p = lut + base;
+    uint32_t run = IDX_EMPTY;
+    for (int i = 0; i < 256; i += 8) {
+        uint32_t k[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) k[m] = p[(size_t)(i + m) * stride];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            run = min(k[m], idx_step(run, 1));
+            p[(size_t)(i + m) * stride] = run;
+        }
+    }
+    run = IDX_EMPTY;
+    for (int i = 255; i >= 0; i -= 8) {
+        uint32_t k[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) k[m] = p[(size_t)(i - m) * stride];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            run = min(k[m], idx_step(run, 1));
+            p[(size_t)(i - m) * stride] = run;
+        }
+    }
+}
+
+int emo_launch_build_index(emo_ctx *ctx) {
+    if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
+    EMO_CK(cudaMemsetAsync(ctx->lut, 0xFF, IDX_CELLS * sizeof(uint32_t), ctx->stream));
+    index_seed_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->lut);
+    EMO_LAUNCH_CHECK(ctx);
+    index_sweep_r_kernel<<<65536 / 8, 256, 0, ctx->stream>>>(ctx->lut);
+    EMO_LAUNCH_CHECK(ctx);
+    index_sweep_kernel<1><<<256, 256, 0, ctx->stream>>>(ctx->lut);
+    EMO_LAUNCH_CHECK(ctx);
+    index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
+    EMO_LAUNCH_CHECK(ctx);
+    ctx->lut_valid = true;
+    return EMO_OK;
+}
+
+bool emo_index_supported(const emo_ctx *ctx) { return ctx->N == 1 && ctx->T <= IDX_INC; }
+
+// ---------------------------------------------------------------------------------------
+// lookup: 4 consecutive pixels (12 bytes) per thread
+// ---------------------------------------------------------------------------------------
+template <bool SRC_WORDS, bool OUT_VEC>
+__global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ lut,
+                                                          uint32_t Q, int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
+    const uint32_t groups = (Q + 3) >> 2;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const uint32_t q0 = g << 2;
+        uint32_t c[4];
+        if (q0 + 4 <= Q) {
+            if (SRC_WORDS) {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (size_t)g * 3;
+                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                c[0] = w0 & 0xFFFFFFu;
+                c[1] = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
+                c[2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
+                c[3] = w2 >> 8;
+            } else {
+                const uint8_t *s = src + (size_t)q0 * 3;
+#pragma unroll
+                for (int m = 0; m < 4; m++) c[m] = s[3 * m] | (uint32_t)s[3 * m + 1] << 8 | (uint32_t)s[3 * m + 2] << 16;
+            }
+            uint32_t k[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) k[m] = __ldg(lut + c[m]);
+            if (OUT_VEC) {
+                // the item map is compose's input (kept in L2); nothing on the device reads dist again
+                *reinterpret_cast<uint4 *>(item + q0) = make_uint4((k[0] & IDX_TILE_MASK) + 1, (k[1] & IDX_TILE_MASK) + 1,
+                                                                   (k[2] & IDX_TILE_MASK) + 1, (k[3] & IDX_TILE_MASK) + 1);
+                stg_cs_v4(dist + q0, make_uint4(k[0] >> IDX_TILE_BITS, k[1] >> IDX_TILE_BITS, k[2] >> IDX_TILE_BITS,
+                                                k[3] >> IDX_TILE_BITS));
+            } else {
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    item[q0 + m] = (int32_t)(k[m] & IDX_TILE_MASK) + 1;
+                    dist[q0 + m] = k[m] >> IDX_TILE_BITS;
+                }
+            }
+        } else {
+            for (uint32_t q = q0; q < Q; q++) {
+                const uint8_t *s = src + (size_t)q * 3;
+                const uint32_t k = __ldg(lut + (s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16));
+                item[q] = (int32_t)(k & IDX_TILE_MASK) + 1;
+                dist[q] = k >> IDX_TILE_BITS;
+            }
+        }
+    }
+}
+
+int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    const uint32_t Q = W * H;  // dim == 1: the source is a flat run of Q pixels
+    const uint32_t groups = (Q + 3) >> 2;
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8 * 4;
+    const uint32_t blocks = min((groups + 255) / 256, cap);
+    const bool sw = (uintptr_t)src % 4 == 0;
+    const bool ov = (uintptr_t)item % 16 == 0 && (uintptr_t)dist % 16 == 0;
+    if (sw && ov) match_index_kernel<true, true><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
+    else if (sw) match_index_kernel<true, false><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
+    else if (ov) match_index_kernel<false, true><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
+    else match_index_kernel<false, false><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
+    EMO_LAUNCH_CHECK(ctx);
+    return EMO_OK;
+}

@@ -545,8 +545,19 @@ static int launch_match_wide(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint3
     return EMO_OK;
 }
 
+// 1to1: answer from the colour-cube index (index.cu) when it exists or is worth building for `queries` blocks — the
+// build plus the lookup cost about as much as scanning 2^31 (block, tile) pairs.  Same results either way.
+int emo_prepare_match(emo_ctx *ctx, uint64_t queries) {
+    if (ctx->match_mode == EMO_MATCH_SCAN || ctx->lut_valid || !emo_index_supported(ctx)) return EMO_OK;
+    if (ctx->match_mode == EMO_MATCH_INDEX || queries * ctx->L >= (1ull << 31)) return emo_launch_build_index(ctx);
+    return EMO_OK;
+}
+
 int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
     if (ctx->wide) return launch_match_wide(ctx, src, W, H, item, dist);
+    int rc = emo_prepare_match(ctx, (uint64_t)(W / ctx->dim) * (H / ctx->dim));
+    if (rc) return rc;
+    if (ctx->match_mode != EMO_MATCH_SCAN && ctx->lut_valid) return emo_launch_match_index(ctx, src, W, H, item, dist);
     MatchParams p;
     p.cand = ctx->cand;
     p.chunk = ctx->chunk;

@@ -103,6 +103,22 @@ int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px,
 int emo_set_library_dev(emo_ctx *ctx, const uint8_t *colors_dev, const uint8_t *tile_px_dev, uint32_t T, uint32_t N,
                         uint32_t ts);
 
+/* ---- (2b) search index (1to1) ---------------------------------------------------------------
+ * The GPU analogue of the KD-tree that TileSet::build_kiddo() (tiles/tileset.rs:178-190) returns and
+ * render_nto1 (rendering.rs:136) builds once per render.  For N == 1 the query space is the 2^24 RGB
+ * colours: emo_build_index computes, for every colour, the tile the scan would pick (exact city-block
+ * distance transform over the colour cube, 64 MiB, same distance and tie-break), after which
+ * emo_match is one table load per pixel.  Results are bit-identical with and without the index.
+ * emo_build_index: builds (or rebuilds) the index of the resident library; EMO_ERR_STATE without a
+ *   library, EMO_ERR_UNSUPPORTED when N != 1 or T > 2^22 (those libraries are always scanned).
+ * emo_set_match_mode: EMO_MATCH_AUTO (default: use the index if it exists, build it on the first
+ *   1to1 match whose scan would cost more than the build, i.e. blocks x tiles >= 2^31),
+ *   EMO_MATCH_SCAN (always the brute-force scan kernel), EMO_MATCH_INDEX (always the index when the
+ *   library supports one).  emo_set_library drops the index. */
+enum { EMO_MATCH_AUTO = 0, EMO_MATCH_SCAN = 1, EMO_MATCH_INDEX = 2 };
+int emo_build_index(emo_ctx *ctx);
+int emo_set_match_mode(emo_ctx *ctx, int mode);
+
 /* ---- (3) nearest-colour match -----------------------------------------------------------
  * Replaces the get_tile closure of render_nto1 (src/mosaic/rendering.rs:158-221):
  * get_img_colors (analysis.rs:23-36) -> coords -> KdTree::nearest_one::<Manhattan>

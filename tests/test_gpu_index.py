@@ -1,0 +1,173 @@
+"""The 1to1 search index (colour-cube table, index.cu) against the oracle and against the scan kernel.
+
+The index is the GPU stand-in for the KD-tree of tileset.rs:178-190; its answers must be the scan's answers
+bit for bit (minimum L1 distance, ties to the smallest tile index)."""
+import numpy as np
+import pytest
+
+import emosaic_b200 as emo
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ictx(ctx):
+    yield ctx
+    ctx.set_match_mode("auto")
+
+
+def both(ctx, src):
+    ctx.set_match_mode("scan")
+    a = ctx.match(src)
+    ctx.set_match_mode("index")
+    b = ctx.match(src)
+    return a, b
+
+
+@pytest.mark.parametrize("T,H,W", [(1, 7, 9), (2, 16, 16), (7, 33, 35), (300, 100, 100), (5000, 64, 257), (70_000, 40, 40)])
+def test_index_matches_oracle(ictx, T, H, W):
+    rng = np.random.default_rng(T)
+    colors = rng.integers(0, 256, (T, 1, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    src[0, 0] = 0
+    src[-1, -1] = 255
+    ictx.set_library(colors)
+    (si, sd), (ii, id_) = both(ictx, src)
+    ri, rd = oracle.match(colors, src) if T * H * W <= 3e9 else oracle.KdTree(colors).match(src)
+    assert (ii == ri).all() and (id_ == rd).all()
+    assert (si == ri).all() and (sd == rd).all()
+
+
+def test_index_every_colour_of_the_cube(ictx):
+    """All 2^24 queries at once: the index output IS the table, checked against the scan kernel cell by cell and
+    against the oracle on a sample."""
+    rng = np.random.default_rng(5)
+    colors = rng.integers(0, 256, (3000, 1, 3), dtype=np.uint8)
+    colors[:8, 0] = [[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [0, 0, 0], [255, 255, 255], [7, 7, 7]]
+    v = np.arange(1 << 24, dtype=np.uint32)
+    src = np.stack([v & 255, (v >> 8) & 255, v >> 16], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    ictx.set_library(colors)
+    (si, sd), (ii, id_) = both(ictx, src)
+    assert (si == ii).all() and (sd == id_).all()
+    rows = rng.choice(4096, 6, replace=False)
+    for r in rows:
+        ri, rd = oracle.match(colors, src[r:r + 1])
+        assert (ii[r:r + 1] == ri).all() and (id_[r:r + 1] == rd).all()
+    assert ii[0, 0] == 1 and ii[-1, -1] == 2  # duplicates (tiles 6 and 7) lose to the smaller index
+
+
+def test_index_ties(ictx):
+    # quantised library: many equidistant tiles at non-zero distance, duplicates of every colour
+    rng = np.random.default_rng(11)
+    colors = (rng.integers(0, 8, (5000, 1, 3)) * 32).astype(np.uint8)
+    src = (rng.integers(0, 8, (96, 96, 3)) * 32 + 16).astype(np.uint8)  # exactly half way between library colours
+    ictx.set_library(colors)
+    (si, sd), (ii, id_) = both(ictx, src)
+    ri, rd = oracle.match(colors, src)
+    assert (ii == ri).all() and (id_ == rd).all() and (si == ri).all()
+    # one axis only: the library lives on the grey diagonal
+    g = rng.integers(0, 256, (400, 1, 1)).astype(np.uint8)
+    colors = np.repeat(g, 3, axis=2)
+    src = rng.integers(0, 256, (50, 60, 3), dtype=np.uint8)
+    ictx.set_library(colors)
+    (si, sd), (ii, id_) = both(ictx, src)
+    ri, rd = oracle.match(colors, src)
+    assert (ii == ri).all() and (id_ == rd).all() and (si == ri).all()
+
+
+def test_index_follows_the_library(ictx):
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (31, 45, 3), dtype=np.uint8)
+    a = rng.integers(0, 256, (500, 1, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (900, 1, 3), dtype=np.uint8)
+    ictx.set_match_mode("index")
+    ictx.set_library(a)
+    ia, _ = ictx.match(src)
+    ictx.set_library(b)       # drops the index of library a
+    ib, db = ictx.match(src)
+    ri, rd = oracle.match(b, src)
+    assert (ib == ri).all() and (db == rd).all()
+    assert (ia == oracle.match(a, src)[0]).all()
+    ictx.build_index()        # explicit rebuild gives the same table
+    ib2, db2 = ictx.match(src)
+    assert (ib2 == ib).all() and (db2 == db).all()
+
+
+def test_index_auto_rule_and_errors(ictx):
+    rng = np.random.default_rng(4)
+    colors = rng.integers(0, 256, (2000, 1, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    ictx.set_match_mode("auto")
+    ictx.set_library(colors)
+    n0 = ictx.launch_count()
+    ictx.match(src)                       # 4096 x 2000 pairs: scanned, no index build
+    assert ictx.launch_count() - n0 <= 3  # the scan kernel (+ key init / finalize when the candidates are split)
+    big = rng.integers(0, 256, (2100, 2100, 3), dtype=np.uint8)   # 4.4 M x 2000 >= 2^31: index built, then used
+    n0 = ictx.launch_count()
+    bi, bd = ictx.match(big)
+    assert ictx.launch_count() - n0 == 5  # seed + 3 sweeps + lookup
+    n0 = ictx.launch_count()
+    i2, d2 = ictx.match(src)              # the index exists now: lookup
+    assert ictx.launch_count() - n0 == 1
+    ri, rd = oracle.match(colors, src)
+    assert (i2 == ri).all() and (d2 == rd).all()
+    sel = big[:3]
+    ri, rd = oracle.match(colors, sel)
+    assert (bi[:3] == ri).all() and (bd[:3] == rd).all()
+    # 4to1 has no colour-cube index
+    c4 = rng.integers(0, 256, (50, 4, 3), dtype=np.uint8)
+    ictx.set_library(c4)
+    with pytest.raises(emo.EmosaicError, match="N == 1"):
+        ictx.build_index()
+    ictx.set_match_mode("index")          # no index for this library: the scan answers
+    q = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+    it, ds = ictx.match(q)
+    ri, rd = oracle.match(c4, q)
+    assert (it == ri).all() and (ds == rd).all()
+    with pytest.raises(emo.EmosaicError, match="unknown mode"):
+        ictx.set_match_mode(7)
+    c2 = emo.Context(0)
+    with pytest.raises(emo.EmosaicError, match="no library"):
+        c2.build_index()
+    c2.close()
+
+
+def test_index_unaligned_and_ragged(ictx):
+    """Odd source address, item/dist at 4-byte (not 16-byte) alignment, Q not a multiple of 4."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(9)
+    colors = rng.integers(0, 256, (777, 1, 3), dtype=np.uint8)
+    ictx.set_library(colors)
+    ictx.set_match_mode("index")
+    for (H, W, so, oo) in [(5, 7, 1, 4), (9, 13, 2, 0), (3, 341, 3, 8), (4, 64, 0, 12), (1, 1, 1, 4), (2, 3, 0, 0)]:
+        src_h = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        raw = torch.zeros(H * W * 3 + 16, dtype=torch.uint8, device=dev)
+        raw[so:so + H * W * 3] = torch.from_numpy(src_h.reshape(-1)).to(dev)
+        item = torch.full((H * W + 16,), -77, dtype=torch.int32, device=dev)
+        dist = torch.full((H * W + 16,), 4242, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ictx.match_dev(raw.data_ptr() + so, W, H, item.data_ptr() + oo, dist.data_ptr() + oo)
+        ictx.sync()
+        o = oo // 4
+        ri, rd = oracle.match(colors, src_h)
+        ih, dh = item.cpu().numpy(), dist.cpu().numpy()
+        assert (ih[o:o + H * W] == ri.reshape(-1)).all() and (dh[o:o + H * W] == rd.reshape(-1)).all()
+        assert (ih[:o] == -77).all() and (ih[o + H * W:] == -77).all()      # nothing written outside [0, Q)
+        assert (dh[:o] == 4242).all() and (dh[o + H * W:] == 4242).all()
+
+
+def test_config4_index_equals_scan_full_size(ictx):
+    """C4 at full size (100 000 tiles, 4096 x 4096 blocks): the table lookup and the 1.7e12-pair scan agree on every block."""
+    rng = np.random.default_rng(1234)
+    colors = rng.integers(0, 256, (100_000, 1, 3), dtype=np.uint8)
+    src = np.random.default_rng(5678).integers(0, 256, (4096, 4096, 3), dtype=np.uint8)
+    ictx.set_library(colors)
+    (si, sd), (ii, id_) = both(ictx, src)
+    assert (si == ii).all() and (sd == id_).all()
+    # clustered library (what averaging random tiles gives: colours within a few units of mid-grey)
+    colors = np.clip(rng.normal(127, 4, (100_000, 1, 3)), 0, 255).astype(np.uint8)
+    ictx.set_library(colors)
+    (si, sd), (ii, id_) = both(ictx, src[:1024])
+    assert (si == ii).all() and (sd == id_).all()
