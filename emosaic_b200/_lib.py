@@ -17,7 +17,7 @@ EXPORTS = [
     "emo_host_alloc", "emo_host_free", "emo_copy_h2d", "emo_copy_d2h", "emo_analyse", "emo_analyse_dev",
     "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_build_index",
     "emo_set_match_mode", "emo_match",
-    "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic",
+    "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev",
     "emo_probe_int_pipe",
 ]
 
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
         "emo_compose_overlay": (C.c_int, [vp, i32p, C.c_uint32, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_compose_overlay_dev": (C.c_int, [vp, i32p, C.c_uint32, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_mosaic": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
+        "emo_mosaic_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
         "emo_probe_int_pipe": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():

@@ -236,6 +236,10 @@ class Context:
         check(self._lib.emo_compose_dev(self._h, C.c_void_p(item_dev), C.c_void_p(src_dev or 0), W, H, out_channels,
                                         tint_alpha, C.c_void_p(out_dev)))
 
+    def mosaic_dev(self, src_dev: int, W: int, H: int, out_channels: int, tint_alpha: int, item_dev: int, dist_dev: int, out_dev: int):
+        check(self._lib.emo_mosaic_dev(self._h, C.c_void_p(src_dev), W, H, out_channels, tint_alpha, C.c_void_p(item_dev),
+                                       C.c_void_p(dist_dev), C.c_void_p(out_dev)))
+
     def mosaic(self, src, out_channels: int = 3, tint_alpha: int = 0, out: np.ndarray | None = None, want_maps=True):
         """Whole path with host buffers: match + compose (+tint)."""
         src = _u8(src)

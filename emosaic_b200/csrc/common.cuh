@@ -39,6 +39,10 @@ void emo_set_error(const char *fmt, ...);
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
+// 1to1 search index keys (index.cu): dist << 22 | tile
+static constexpr uint32_t EMO_IDX_TILE_BITS = 22;
+static constexpr uint32_t EMO_IDX_TILE_MASK = (1u << EMO_IDX_TILE_BITS) - 1;
+
 struct emo_tint_tables {
     int alpha = -1;           // alpha the tables were built for (-1: none)
     int K = 0;                // max exceptional bg values per fg (see compose.cu)
@@ -165,6 +169,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // TMA 1-D bulk copy shared -> global (bulk async-group completion)
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+// L2 eviction-priority policies (createpolicy) and the loads / stores that carry them
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg_nc_hint_u32(const void *p, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg_hint_v4(void *p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit_wait_read() {

@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(192) compose_tile_kernel(const uint8_t *__rest
     const size_t OWB = (size_t)bw * RB;
     uint8_t *d = out + (size_t)by * TS * OWB + (size_t)bx0 * RB;
     if (threadIdx.x < TS) {
-        bulk_s2g(d + (size_t)threadIdx.x * OWB, sm + threadIdx.x * STRIDE, ROW_CHUNK);
+        // the output is written once and never read on the device: first in line for eviction, so that the tile
+        // library, the item map and the search index keep their place in L2 (C4 compose: 514 -> 500 us)
+        bulk_s2g_hint(d + (size_t)threadIdx.x * OWB, sm + threadIdx.x * STRIDE, ROW_CHUNK, l2_policy_evict_first());
         bulk_commit_wait_read();  // shared memory must stay alive until the engine has read it
     }
 }

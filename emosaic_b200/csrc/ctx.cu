@@ -512,6 +512,27 @@ int emo_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t 
 // Whole path with host buffers: the source goes up once, then block-row chunks are matched and
 // composed on the compute stream while the previous chunk's output drains to the host on the
 // copy stream (two device output buffers).
+// match + compose of one (stripe of an) image, device pointers, back to back on the ctx stream
+static int mosaic_launch(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha, int32_t *item,
+                         uint32_t *dist, uint8_t *out) {
+    int rc = emo_launch_match(ctx, src, W, H, item, dist);
+    if (rc) return rc;
+    return emo_launch_compose(ctx, item, src, W, H, oc, tint_alpha, out);
+}
+
+int emo_mosaic_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha, int32_t *item,
+                   uint32_t *dist, uint8_t *out) {
+    int rc = check_match_args(ctx, src, W, H);
+    if (rc) return rc;
+    EMO_REQUIRE(item && dist, EMO_ERR_ARG, "mosaic: item/dist is NULL");
+    EMO_REQUIRE((uintptr_t)item % 4 == 0 && (uintptr_t)dist % 4 == 0, EMO_ERR_ARG, "mosaic: item/dist must be 4-byte aligned");
+    if ((rc = check_compose_args(ctx, item, src, W, H, oc, out))) return rc;
+    EMO_REQUIRE(oc == 3 || (uintptr_t)out % 4 == 0, EMO_ERR_ARG, "mosaic: RGBA output must be 4-byte aligned");
+    EMO_CK(cudaSetDevice(ctx->device));
+    if ((rc = emo_prepare_match(ctx, (uint64_t)(W / ctx->dim) * (H / ctx->dim)))) return rc;
+    return mosaic_launch(ctx, src, W, H, oc, tint_alpha, item, dist, out);
+}
+
 int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha,
                int32_t *item, uint32_t *dist, uint8_t *out) {
     int rc = check_match_args(ctx, src, W, H);
@@ -547,10 +568,10 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
         uint32_t nr = bh - r0 < rows_per_chunk ? bh - r0 : rows_per_chunk;
         const uint8_t *s = dsrc + (size_t)r0 * dim * W * 3;
         int b = k & 1;
-        if ((rc = emo_launch_match(ctx, s, W, nr * dim, ditem + (size_t)r0 * bw, ddist + (size_t)r0 * bw))) return rc;
         // the buffer must have drained (chunk k-2) before it is overwritten
         if (k >= 2) EMO_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[2 + b], 0));
-        if ((rc = emo_launch_compose(ctx, ditem + (size_t)r0 * bw, s, W, nr * dim, oc, tint_alpha, dout[b]))) return rc;
+        if ((rc = mosaic_launch(ctx, s, W, nr * dim, oc, tint_alpha, ditem + (size_t)r0 * bw, ddist + (size_t)r0 * bw, dout[b])))
+            return rc;
         EMO_CK(cudaEventRecord(ctx->ev_pipe[b], ctx->stream));
         EMO_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[b], 0));
         EMO_CK(cudaMemcpyAsync(out + (size_t)r0 * row_out, dout[b], (size_t)nr * row_out, cudaMemcpyDeviceToHost,

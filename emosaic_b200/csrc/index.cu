@@ -22,9 +22,9 @@
 // 8 B written per query plus one L2-resident gather.
 #include "common.cuh"
 
-static constexpr uint32_t IDX_TILE_BITS = 22;
+static constexpr uint32_t IDX_TILE_BITS = EMO_IDX_TILE_BITS;
 static constexpr uint32_t IDX_INC = 1u << IDX_TILE_BITS;
-static constexpr uint32_t IDX_TILE_MASK = IDX_INC - 1;
+static constexpr uint32_t IDX_TILE_MASK = EMO_IDX_TILE_MASK;
 static constexpr uint32_t IDX_EMPTY = 0xFFFFFFFFu;
 static constexpr size_t IDX_CELLS = (size_t)1 << 24;
 
@@ -139,13 +139,15 @@ template <bool SRC_WORDS, bool OUT_VEC>
 __global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ lut,
                                                           uint32_t Q, int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
     const uint32_t groups = (Q + 3) >> 2;
+    // L2 priorities: the table is what should stay, the source and the dist map pass through once
+    const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
         const uint32_t q0 = g << 2;
         uint32_t c[4];
         if (q0 + 4 <= Q) {
             if (SRC_WORDS) {
                 const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (size_t)g * 3;
-                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                const uint32_t w0 = ldg_nc_hint_u32(w, drop), w1 = ldg_nc_hint_u32(w + 1, drop), w2 = ldg_nc_hint_u32(w + 2, drop);
                 c[0] = w0 & 0xFFFFFFu;
                 c[1] = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
                 c[2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
@@ -157,13 +159,13 @@ __global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restr
             }
             uint32_t k[4];
 #pragma unroll
-            for (int m = 0; m < 4; m++) k[m] = __ldg(lut + c[m]);
+            for (int m = 0; m < 4; m++) k[m] = ldg_nc_hint_u32(lut + c[m], keep);
             if (OUT_VEC) {
                 // the item map is compose's input (kept in L2); nothing on the device reads dist again
                 *reinterpret_cast<uint4 *>(item + q0) = make_uint4((k[0] & IDX_TILE_MASK) + 1, (k[1] & IDX_TILE_MASK) + 1,
                                                                    (k[2] & IDX_TILE_MASK) + 1, (k[3] & IDX_TILE_MASK) + 1);
-                stg_cs_v4(dist + q0, make_uint4(k[0] >> IDX_TILE_BITS, k[1] >> IDX_TILE_BITS, k[2] >> IDX_TILE_BITS,
-                                                k[3] >> IDX_TILE_BITS));
+                const uint4 dv = make_uint4(k[0] >> IDX_TILE_BITS, k[1] >> IDX_TILE_BITS, k[2] >> IDX_TILE_BITS, k[3] >> IDX_TILE_BITS);
+                stg_hint_v4(dist + q0, dv, drop);
             } else {
 #pragma unroll
                 for (int m = 0; m < 4; m++) {

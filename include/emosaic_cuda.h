@@ -154,11 +154,16 @@ int emo_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t 
 int emo_compose_overlay_dev(emo_ctx *ctx, const int32_t *item_dev, uint32_t W, uint32_t H, const uint8_t *overlay_dev,
                             uint32_t ow, uint32_t oh, uint8_t tint_alpha, uint8_t *out_dev);
 
-/* ---- whole path, host buffers ------------------------------------------------------------
- * render_nto1 (+ tint) in one call: H2D(src) -> match -> compose -> D2H(out) with the copies
- * pipelined against the kernels in block-row chunks. item/dist may be NULL. */
+/* ---- whole path ------------------------------------------------------------------------------
+ * render_nto1 (+ tint) in one call (rendering.rs:124-239 + main.rs:447-478).
+ * emo_mosaic: host buffers; H2D(src) -> match -> compose -> D2H(out) with the copies pipelined
+ *   against the kernels in block-row chunks. item/dist may be NULL.
+ * emo_mosaic_dev: device buffers, asynchronous on the ctx stream: emo_match_dev followed by
+ *   emo_compose_dev in one call (item_dev and dist_dev are required). */
 int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t out_channels,
                uint8_t tint_alpha, int32_t *item, uint32_t *dist, uint8_t *out);
+int emo_mosaic_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, uint32_t out_channels,
+                   uint8_t tint_alpha, int32_t *item_dev, uint32_t *dist_dev, uint8_t *out_dev);
 
 /* ---- measurement helpers ------------------------------------------------------------------
  * Integer-pipe microbenchmark used as the roofline denominator of the match kernel:

@@ -171,3 +171,73 @@ def test_config4_index_equals_scan_full_size(ictx):
     ictx.set_library(colors)
     (si, sd), (ii, id_) = both(ictx, src[:1024])
     assert (si == ii).all() and (sd == id_).all()
+
+
+@pytest.mark.parametrize("ts,bh,bw", [(8, 5, 128), (8, 33, 64), (16, 7, 96), (16, 3, 32), (8, 4, 100), (32, 3, 16), (6, 5, 64)])
+def test_mosaic_dev(ictx, ts, bh, bw):
+    """emo_mosaic_dev (device-resident match + compose in one call) with the index, with tint and with the scan; canaries
+    around all three outputs."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(ts * 1000 + bw)
+    T = 500
+    tiles_h = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+    colors = ictx.analyse_tiles(tiles_h, 1)
+    src_h = rng.integers(0, 256, (bh, bw, 3), dtype=np.uint8)
+    ictx.set_library(colors, tiles_h)
+    ictx.set_match_mode("index")
+    ictx.build_index()
+    Q, OB = bh * bw, bh * ts * bw * ts * 3
+    src = torch.from_numpy(src_h.reshape(-1)).to(dev)
+    item = torch.full((Q + 32,), -77, dtype=torch.int32, device=dev)
+    dist = torch.full((Q + 32,), 4242, dtype=torch.int32, device=dev)
+    out = torch.full((OB + 64,), 0xA5, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    n0 = ictx.launch_count()
+    ictx.mosaic_dev(src.data_ptr(), bw, bh, 3, 0, item.data_ptr() + 64, dist.data_ptr() + 64, out.data_ptr() + 32)
+    ictx.sync()
+    assert ictx.launch_count() - n0 == 2
+    ri, rd = oracle.match(colors, src_h)
+    ih, dh, oh = item.cpu().numpy(), dist.cpu().numpy(), out.cpu().numpy()
+    assert (ih[16:16 + Q] == ri.reshape(-1)).all() and (dh[16:16 + Q] == rd.reshape(-1)).all()
+    assert (oh[32:32 + OB].reshape(bh * ts, bw * ts, 3) == oracle.render(tiles_h, ri)).all()
+    assert (ih[:16] == -77).all() and (ih[16 + Q:] == -77).all() and (dh[:16] == 4242).all() and (dh[16 + Q:] == 4242).all()
+    assert (oh[:32] == 0xA5).all() and (oh[32 + OB:] == 0xA5).all()
+    # tint (RGBA) and the scan mode go through the two-kernel path of the same call
+    out4 = torch.zeros(bh * ts * bw * ts * 4, dtype=torch.uint8, device=dev)
+    ictx.mosaic_dev(src.data_ptr(), bw, bh, 4, 127, item.data_ptr(), dist.data_ptr(), out4.data_ptr())
+    ictx.sync()
+    assert (out4.cpu().numpy().reshape(bh * ts, bw * ts, 4) == oracle.tint(oracle.render(tiles_h, ri), src_h, 127)).all()
+    ictx.set_match_mode("scan")
+    out.fill_(0)
+    ictx.mosaic_dev(src.data_ptr(), bw, bh, 3, 0, item.data_ptr(), dist.data_ptr(), out.data_ptr())
+    ictx.sync()
+    assert (item.cpu().numpy()[:Q] == ri.reshape(-1)).all()
+    assert (out.cpu().numpy()[:OB].reshape(bh * ts, bw * ts, 3) == oracle.render(tiles_h, ri)).all()
+
+
+def test_mosaic_dev_4to1_and_errors(ictx):
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(21)
+    tiles_h = rng.integers(0, 256, (120, 16, 16, 3), dtype=np.uint8)
+    colors = ictx.analyse_tiles(tiles_h, 2)
+    src_h = rng.integers(0, 256, (12, 64, 3), dtype=np.uint8)
+    ictx.set_library(colors, tiles_h)
+    src = torch.from_numpy(src_h.reshape(-1)).to(dev)
+    item = torch.zeros(6 * 32, dtype=torch.int32, device=dev)
+    dist = torch.zeros(6 * 32, dtype=torch.int32, device=dev)
+    out = torch.zeros(6 * 16 * 32 * 16 * 3, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    ictx.mosaic_dev(src.data_ptr(), 64, 12, 3, 0, item.data_ptr(), dist.data_ptr(), out.data_ptr())
+    ictx.sync()
+    ri, rd = oracle.match(colors, src_h)
+    assert (item.cpu().numpy().reshape(6, 32) == ri).all() and (dist.cpu().numpy().reshape(6, 32) == rd).all()
+    assert (out.cpu().numpy().reshape(96, 512, 3) == oracle.render(tiles_h, ri)).all()
+    with pytest.raises(emo.EmosaicError, match="item/dist is NULL"):
+        ictx.mosaic_dev(src.data_ptr(), 64, 12, 3, 0, 0, dist.data_ptr(), out.data_ptr())
+    with pytest.raises(emo.EmosaicError, match="divisible by 2"):
+        ictx.mosaic_dev(src.data_ptr(), 63, 12, 3, 0, item.data_ptr(), dist.data_ptr(), out.data_ptr())
+    ictx.set_library(colors)   # no tile pixels
+    with pytest.raises(emo.EmosaicError, match="no tile pixels"):
+        ictx.mosaic_dev(src.data_ptr(), 64, 12, 3, 0, item.data_ptr(), dist.data_ptr(), out.data_ptr())
