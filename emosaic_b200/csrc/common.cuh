@@ -116,6 +116,23 @@ int emo_launch_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, ui
 // device helpers
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// launch with programmatic stream serialization (see grid_dependency_wait)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t emo_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -171,6 +188,10 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+// Programmatic dependent launch: the kernel may be scheduled while the previous kernel of the stream drains; it must
+// not touch that kernel's results before grid_dependency_wait() (a no-op for a normally launched kernel).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // L2 eviction-priority policies (createpolicy) and the loads / stores that carry them
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;

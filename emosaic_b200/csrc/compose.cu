@@ -20,6 +20,8 @@
 // q = (X + (X >> 8)) >> 8, and applies the exceptions branch-free by decrementing an exceptional
 // bg byte before the multiply (bg-1 gives exactly q-1).  Alphas with more than 3 exceptional bg per
 // fg (32 of 254) and odd geometries use the generic kernel, which reads the exact table.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(192) compose_tile_kernel(const uint8_t *__rest
     const uint32_t by = blockIdx.y, bx0 = blockIdx.x * G;
     const int part = threadIdx.x % PPT, tile0 = threadIdx.x / PPT;
     const int32_t *it = item + (size_t)by * bw + bx0 + tile0;
+    grid_dependency_wait();  // the item map comes from the kernel before this one
     uint4 v[PASSES];
 #pragma unroll
     for (int k = 0; k < PASSES; k++) {
@@ -338,11 +341,14 @@ int emo_launch_compose(emo_ctx *ctx, const int32_t *item, const uint8_t *src, ui
     const uint32_t ts = ctx->ts, dim = ctx->dim, bw = W / dim, bh = H / dim, T = ctx->T;
     const uint32_t RB = ts * 3;
     const bool aligned = ((uintptr_t)out % 16 == 0) && bh <= 65535;
+    static const bool pdl = !(getenv("EMO_PDL") && atoi(getenv("EMO_PDL")) == 0);  // EMO_PDL=0: plain launches
     if (oc == 3) {
         if (aligned && ts == 8 && bw % 64 == 0) {
-            compose_tile_kernel<8><<<dim3(bw / 64, bh), 192, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
+            if (pdl) EMO_CK(emo_launch_pdl(compose_tile_kernel<8>, dim3(bw / 64, bh), dim3(192), 0, ctx->stream, ctx->lib_px, item, T, bw, out, ctx->err_flag));
+            else compose_tile_kernel<8><<<dim3(bw / 64, bh), 192, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
         } else if (aligned && ts == 16 && bw % 32 == 0) {
-            compose_tile_kernel<16><<<dim3(bw / 32, bh), 192, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
+            if (pdl) EMO_CK(emo_launch_pdl(compose_tile_kernel<16>, dim3(bw / 32, bh), dim3(192), 0, ctx->stream, ctx->lib_px, item, T, bw, out, ctx->err_flag));
+            else compose_tile_kernel<16><<<dim3(bw / 32, bh), 192, 0, ctx->stream>>>(ctx->lib_px, item, T, bw, out, ctx->err_flag);
         } else if (aligned && RB % 16 == 0) {
             const uint32_t pieces = bw * RB / 16;
             compose_copy_kernel<uint4><<<dim3((pieces + 255) / 256, bh), 256, 0, ctx->stream>>>(ctx->lib_px, item, T, ts, bw, out,

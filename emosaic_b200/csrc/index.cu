@@ -20,6 +20,8 @@
 // read as a little-endian word), 64 MiB, resident in the 126 MB L2 while the source streams through.
 // Cost: build = 1 memset + 4 small kernels (about 0.1 ms, once per library); lookup = 3 B read +
 // 8 B written per query plus one L2-resident gather.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static constexpr uint32_t IDX_TILE_BITS = EMO_IDX_TILE_BITS;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restr
     const uint32_t groups = (Q + 3) >> 2;
     // L2 priorities: the table is what should stay, the source and the dist map pass through once
     const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+    grid_dependency_wait();  // the previous kernel of the stream may still be reading the item map this one rewrites
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
         const uint32_t q0 = g << 2;
         uint32_t c[4];
@@ -191,7 +194,9 @@ int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_
     const uint32_t blocks = min((groups + 255) / 256, cap);
     const bool sw = (uintptr_t)src % 4 == 0;
     const bool ov = (uintptr_t)item % 16 == 0 && (uintptr_t)dist % 16 == 0;
-    if (sw && ov) match_index_kernel<true, true><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
+    static const bool pdl = !(getenv("EMO_PDL") && atoi(getenv("EMO_PDL")) == 0);  // EMO_PDL=0: plain launches
+    if (sw && ov && pdl) EMO_CK(emo_launch_pdl(match_index_kernel<true, true>, dim3(blocks), dim3(256), 0, ctx->stream, src, (const uint32_t *)ctx->lut, Q, item, dist));
+    else if (sw && ov) match_index_kernel<true, true><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
     else if (sw) match_index_kernel<true, false><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
     else if (ov) match_index_kernel<false, true><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
     else match_index_kernel<false, false><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
