@@ -347,8 +347,8 @@ def run_ours(args):
             "achieved": comp_bytes / (comp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": comp_bytes / (comp_ms * 1e-3) / 1e9 / hbm_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload at N=1, from the committed
-            # ncu --set full capture profiles/r01e_ncu_full_compose_tile_kernel.txt (95.4 MB + 3162.8 MB)
-            "traffic": 3258187696 if world == 1 else None,
+            # ncu --set full capture profiles/r01g_ncu_full_compose_tile_kernel.txt (78.3 MB + 3162.6 MB)
+            "traffic": 3240965504 if world == 1 else None,
             "peak_source": peak_src, "ms_per_launch": comp_ms, "share_of_step": comp_ms / (comp_ms + match_ms),
             "note": "achieved = (output stripe + item map + tile library once) bytes / CUDA-event time of the compose "
                     "launch (avg over the timed steps, rank 0)",

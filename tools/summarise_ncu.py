@@ -32,6 +32,7 @@ KEYS = [
 def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.OrderedDict()
+    by_grid = collections.OrderedDict()
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
@@ -40,10 +41,20 @@ def launches(path):
         u = row["Metric Unit"]
         v = v / 1e3 if u in ("nsecond", "ns") else (v * 1e3 if u in ("msecond", "ms") else v)
         agg.setdefault(name, []).append(v)
+        by_grid.setdefault((name, row.get("Grid Size", "")), []).append(v)
     tot = sum(sum(v) for v in agg.values())
     print(f"{'kernel':72s} {'n':>5s} {'total_us':>12s} {'avg_us':>10s} {'share':>6s}")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         print(f"{k[:72]:72s} {len(v):5d} {sum(v):12.1f} {sum(v) / len(v):10.1f} {sum(v) / tot:6.3f}")
+    # kernels launched with several grid sizes (e.g. the full-stripe launches of the timed steps vs the chunked launches
+    # of emo_mosaic): one line per grid
+    multi = {k for k, _ in by_grid if sum(1 for kk, _ in by_grid if kk == k) > 1}
+    if multi:
+        print()
+        print(f"{'kernel, by grid size':60s} {'grid':>18s} {'n':>5s} {'avg_us':>10s}")
+        for (k, g), v in by_grid.items():
+            if k in multi:
+                print(f"{k[:60]:60s} {g:>18s} {len(v):5d} {sum(v) / len(v):10.1f}")
 
 
 def report(path):
