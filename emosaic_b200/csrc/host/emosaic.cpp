@@ -28,6 +28,8 @@ void check(int rc) {
 
 Context::Context(int device) { check(emo_create(device, &h_)); }
 Context::~Context() { emo_destroy(h_); }
+void Context::build_index() const { check(emo_build_index(h_)); }
+void Context::set_match_mode(int mode) const { check(emo_set_match_mode(h_, mode)); }
 
 // ---- tiles/utils.rs:18-43 ------------------------------------------------------------------------
 void flipped_coords(std::vector<uint32_t> &coords) {

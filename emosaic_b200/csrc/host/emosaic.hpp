@@ -52,6 +52,9 @@ public:
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
     emo_ctx *handle() const { return h_; }
+    // 1to1 search index (include/emosaic_cuda.h §2b): built on demand by the match; these force or forbid it
+    void build_index() const;
+    void set_match_mode(int mode) const;  // EMO_MATCH_AUTO | EMO_MATCH_SCAN | EMO_MATCH_INDEX
 
 private:
     emo_ctx *h_ = nullptr;

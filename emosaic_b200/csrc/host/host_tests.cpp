@@ -200,6 +200,30 @@ int main(int argc, char **argv) {
             CHECK(throws_with([&] { render_nto1(ctx, uni[0], ts, dim, true); }, "outside the accelerated path"));
         });
     }
+    // the 1to1 search index answers exactly like the scan (include/emosaic_cuda.h §2b)
+    run("test_search_index_equals_scan", [&] {
+        TileSet ts(1);
+        uint32_t seed = 12345;
+        auto rnd = [&] { seed = seed * 1664525u + 1013904223u; return (uint8_t)(seed >> 24); };
+        for (int i = 0; i < 500; i++) {
+            const uint8_t r = rnd(), g = rnd(), b = rnd();
+            Image tile(8, 8, 3);
+            for (size_t k = 0; k < tile.data.size(); k += 3) { tile.data[k] = r; tile.data[k + 1] = g; tile.data[k + 2] = b; }
+            ts.push_tile_with_image("", {r, g, b}, tile);
+        }
+        Image src(64, 48, 3);
+        for (auto &v : src.data) v = rnd();
+        ctx.set_match_mode(EMO_MATCH_SCAN);
+        RenderResult a = render_nto1(ctx, src, ts, 8);
+        ctx.set_match_mode(EMO_MATCH_INDEX);
+        RenderResult b = render_nto1(ctx, src, ts, 8);
+        ctx.set_match_mode(EMO_MATCH_AUTO);
+        CHECK(a.image == b.image && a.item == b.item && a.dist == b.dist);
+        TileSet four(4);
+        four.push_tile_with_image("", std::vector<uint8_t>(12, 0), Image(8, 8, 3));
+        four.build_kiddo(ctx, 8);
+        CHECK(throws_with([&] { ctx.build_index(); }, "N == 1"));
+    });
     // main.rs:603-615 exits become errors
     run("test_dimension_rules", [&] {
         TileSet ts(4);
