@@ -105,3 +105,25 @@ def tint(mosaic: np.ndarray, src: np.ndarray, A: int) -> np.ndarray:
     out[..., :3] = rgb
     out[..., 3] = a
     return out
+
+
+def l1_voronoi_table(colors: np.ndarray, bits: int = 8):
+    """Restatement (numpy, test infrastructure) of the construction in emosaic_b200/csrc/index.cu on a cube with
+    `bits` bits per channel: for every colour of the cube the (L1 distance, tile) of the tile a scan with strict `<`
+    would keep — minimum distance, ties to the smallest tile index.  Exact city-block distance transform: seed the
+    library colours with key = dist << 22 | tile, then one forward/backward min-plus sweep per axis.
+    colors [T,1,3] with values < 2**bits.  Returns (tile [S,S,S] int64 0-based indexed [b][g][r], dist [S,S,S])."""
+    S = 1 << bits
+    INC = 1 << 22
+    EMPTY = np.int64(1) << 40
+    lut = np.full((S, S, S), EMPTY, dtype=np.int64)          # [b][g][r]
+    c = colors.reshape(-1, 3).astype(np.int64)
+    for t in range(c.shape[0] - 1, -1, -1):                   # descending, so the smallest tile index is written last
+        lut[c[t, 2], c[t, 1], c[t, 0]] = t
+    for axis in (2, 1, 0):                                    # r (contiguous), g, b
+        a = np.moveaxis(lut, axis, 0)
+        for i in range(1, S):
+            a[i] = np.minimum(a[i], a[i - 1] + INC)
+        for i in range(S - 2, -1, -1):
+            a[i] = np.minimum(a[i], a[i + 1] + INC)
+    return lut & (INC - 1), lut >> 22
