@@ -366,6 +366,9 @@ def run_ours(args):
         achieved = ops / (scan_ms * 1e-3)
         extra = {
             "match_ms": match_ms_max, "compose_ms": comp_ms_max, "index_build_ms": index_build_ms,
+            # the per-library work is outside the step on both arms (KD-tree build on the CPU arm, index build here);
+            # for reference, the figure if every step rebuilt the index as rendering.rs:136 rebuilds the tree per render
+            "value_if_index_rebuilt_every_step": Q_total / ((ms / args.steps + index_build_ms) * 1e-3),
             "composed_output_gbs": (H * ts * W * ts * 3) / (comp_ms_max * 1e-3) / 1e9,
             "roofline_match_index": {"kernel": "match_index_kernel", "bound": "hbm", "achieved": look_bytes / (match_ms * 1e-3) / 1e9,
                                      "peak": hbm_peak, "unit": "GB/s", "frac": look_bytes / (match_ms * 1e-3) / 1e9 / hbm_peak,
