@@ -211,6 +211,7 @@ analyse_small_kernel(const uint8_t *__restrict__ tiles, uint64_t T, uint8_t *__r
     constexpr int LPT = 32 / TPS;                      // lanes per tile: 16 / 4
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool out4_words = OUT4 && (reinterpret_cast<uintptr_t>(out4) & 3) == 0;
     uint8_t *ring = smem + (size_t)warp * STAGES * STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * STAGES * STAGE_BYTES) + warp * STAGES;
     if (lane == 0) {
@@ -260,11 +261,28 @@ analyse_small_kernel(const uint8_t *__restrict__ tiles, uint64_t T, uint8_t *__r
             }
         }
         constexpr uint32_t CELL_PX = (TS / 2) * (TS / 2);
-        const int crow = (lane / CR_LANES) & 1;
-        if (OUT4 && tile < T && (lane % CR_LANES) == 0) {
-            uint8_t *o = out4 + tile * 12 + crow * 6;
-            o[0] = (uint8_t)(L[0] / CELL_PX); o[1] = (uint8_t)(L[1] / CELL_PX); o[2] = (uint8_t)(L[2] / CELL_PX);
-            o[3] = (uint8_t)(Rr[0] / CELL_PX); o[4] = (uint8_t)(Rr[1] / CELL_PX); o[5] = (uint8_t)(Rr[2] / CELL_PX);
+        if (OUT4) {
+            // the 6 bytes of this lane's cell row in two words; the first lane of a tile fetches the other cell row's
+            // pair and writes the tile's 12 bytes as three words (a tile's output is 4-byte aligned when out4 is)
+            const uint32_t w0 = (L[0] / CELL_PX) | (L[1] / CELL_PX) << 8 | (L[2] / CELL_PX) << 16 | (Rr[0] / CELL_PX) << 24;
+            const uint32_t w1 = (Rr[1] / CELL_PX) | (Rr[2] / CELL_PX) << 8;
+            const uint32_t x0 = __shfl_down_sync(0xffffffffu, w0, CR_LANES), x1 = __shfl_down_sync(0xffffffffu, w1, CR_LANES);
+            if (tile < T && (lane % LPT) == 0) {
+                if (out4_words) {
+                    uint32_t *o = reinterpret_cast<uint32_t *>(out4 + tile * 12);
+                    o[0] = w0;
+                    o[1] = w1 | x0 << 16;
+                    o[2] = x0 >> 16 | x1 << 16;
+                } else {
+                    uint8_t *o = out4 + tile * 12;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) o[k] = (uint8_t)(w0 >> (8 * k));
+                    o[4] = (uint8_t)w1; o[5] = (uint8_t)(w1 >> 8);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) o[6 + k] = (uint8_t)(x0 >> (8 * k));
+                    o[10] = (uint8_t)x1; o[11] = (uint8_t)(x1 >> 8);
+                }
+            }
         }
         if (OUT1) {
 #pragma unroll

@@ -15,7 +15,7 @@ for ts, T in ((8, 16_000_000), (16, 4_000_000), (32, 2_000_000), (64, 500_000)):
                            ("fused", lambda: ctx.analyse_fused_dev(tiles.data_ptr(), T, ts, o1.data_ptr(), o4.data_ptr()), 15)):
         fn(); ctx.sync()
         t = []
-        for _ in range(5):
+        for _ in range(9):  # single launches vary by up to 1.6x on this pool (0.47 .. 0.78 ms at ts=8): median of 9
             ctx.timer_start(); fn(); t.append(ctx.timer_stop())
         ms = float(np.median(t))
         print(f"ts={ts:3d} T={T:9d} {name:5s}: {ms:7.3f} ms  {T*(ts*ts*3+outb)/(ms*1e-3)/1e9:8.1f} GB/s")
