@@ -337,6 +337,7 @@ def run_ours(args):
     ctx.host_free(out_pin)
 
     hbm_peak, peak_src = peaks()
+    c3_sharded = c3_across_ranks(ctx, torch, dist, dev, world, rank, max_over_ranks, barrier) if world > 1 and not args.no_extras else None
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel of the step: compose_tile_kernel<8> (HBM writes) -----------
@@ -391,6 +392,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_extras:
             extra.update(extras(ctx, torch, dev, hbm_peak, peak_src))
+        if c3_sharded is not None:
+            extra["c3_analysis_sharded"] = c3_sharded
         cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
         if cpu is not None:
             extra["cpu_baseline_spread_library"] = cpu_baseline_spread(cfg)
@@ -415,6 +418,54 @@ def run_ours(args):
     if line is not None:
         emit(line)
     ctx.close()
+
+
+def c3_across_ranks(ctx, torch, dist, dev, world, rank, max_over_ranks, barrier):
+    """C3 (analysis cache build, 1M tiles of 64x64, fused 1to1+4to1) sharded over the ranks: every rank analyses
+    its contiguous range of tiles, one NCCL all_gather per output assembles [T,3] and [T,12] on every rank.  Timed on the
+    device (kernel + collectives on one stream), max over ranks.  Outside the timed region of the headline number."""
+    from emosaic_b200 import sharding
+    T3, ts3 = 1_000_000, 64
+    a, b = sharding.stripe_bounds(T3, world, rank)
+    n = b - a
+    ok = torch.ones(1, device=dev)
+    try:
+        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+        tiles = torch.randint(0, 256, (n * ts3 * ts3 * 3,), dtype=torch.uint8, device=dev, generator=g)
+        o1 = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+        o4 = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+    except Exception:  # noqa: BLE001  (e.g. out of memory on one rank: nobody enters the collective)
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) == 0.0:
+        return {"error": "allocation failed on a rank"}
+    stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream that both torch/NCCL and the library can use
+    torch.cuda.synchronize()
+    ctx.sync()
+    ctx.set_stream(stream.cuda_stream)          # kernel and collectives on one stream, bracketed by one pair of events
+    times, k_times = [], []
+    try:
+        with torch.cuda.stream(stream):
+            for rep in range(4):
+                barrier()
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record(stream)
+                ctx.analyse_fused_dev(tiles.data_ptr(), n, ts3, o1.data_ptr(), o4.data_ptr())
+                e1.record(stream)
+                f1 = sharding.gather_analysis(o1, T3, 3, world, rank)
+                f4 = sharding.gather_analysis(o4, T3, 12, world, rank)
+                e2.record(stream)
+                torch.cuda.synchronize()
+                if rep:                                   # first pass warms NCCL up
+                    times.append(max_over_ranks(e0.elapsed_time(e2)))
+                    k_times.append(max_over_ranks(e0.elapsed_time(e1)))
+            same = bool((f1[a * 3:b * 3] == o1).all()) and bool((f4[a * 12:b * 12] == o4).all()) and f1.numel() == T3 * 3
+    finally:
+        torch.cuda.synchronize()
+        ctx.set_stream(None)
+    ms, kms = float(np.median(times)), float(np.median(k_times))
+    return {"tiles": T3, "ranks": world, "ms": ms, "kernel_ms": kms, "allgather_ms": ms - kms, "tiles_per_s": T3 / (ms * 1e-3),
+            "input_gbs_whole_job": T3 * 12303 / (ms * 1e-3) / 1e9, "own_range_intact_after_gather": same}
 
 
 def extras(ctx, torch, dev, hbm_peak, peak_src):

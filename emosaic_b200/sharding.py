@@ -27,3 +27,32 @@ def source_stripe(src, dim: int, world: int, rank: int):
     bh = src.shape[0] // dim
     a, b = stripe_bounds(bh, world, rank)
     return src[a * dim:b * dim], (a, b)
+
+
+def gather_analysis(local, T: int, bytes_per_tile: int, world: int, rank: int, group=None):
+    """Analysis cache build across GPUs (SURVEY §8e, C3): rank r analysed the tiles of `stripe_bounds(T, world, r)`;
+    all-gather the per-tile results (`bytes_per_tile` = 3*N) so every rank holds colours [T, bytes_per_tile].
+
+    `local` is a flat uint8 torch tensor (CUDA with the NCCL backend, CPU with gloo) of this rank's
+    (stop - start) * bytes_per_tile bytes.  Ranges differ by at most one tile, so shards are padded to the
+    largest and trimmed after the collective — one all_gather, no other exchange."""
+    import torch
+    import torch.distributed as dist
+
+    a, b = stripe_bounds(T, world, rank)
+    if local.numel() != (b - a) * bytes_per_tile:
+        raise ValueError(f"rank {rank}: expected {(b - a) * bytes_per_tile} bytes, got {local.numel()}")
+    if world == 1:
+        return local
+    cap = (T + world - 1) // world * bytes_per_tile
+    padded = torch.zeros(cap, dtype=torch.uint8, device=local.device)
+    padded[:local.numel()] = local
+    out = torch.empty(world * cap, dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    if T % world == 0:
+        return out
+    parts = []
+    for r in range(world):
+        ra, rb = stripe_bounds(T, world, r)
+        parts.append(out[r * cap:r * cap + (rb - ra) * bytes_per_tile])
+    return torch.cat(parts)

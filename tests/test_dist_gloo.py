@@ -78,3 +78,37 @@ def test_two_rank_stripes(N):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _analysis_worker(rank, world, port, T, q):
+    sys.path.insert(0, ROOT)
+    import oracle
+    from emosaic_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ts = 8
+    tiles = np.random.default_rng(77).integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)   # same seed on every rank
+    a, b = sharding.stripe_bounds(T, world, rank)
+    ok = True
+    for N in (1, 4):
+        local = oracle.analyse_tiles(tiles[a:b], N)            # the oracle stands in for emo_analyse on this rank's range
+        full = sharding.gather_analysis(torch.from_numpy(local.reshape(-1)), T, 3 * N, world, rank)
+        ok = ok and (full.numpy().reshape(T, N, 3) == oracle.analyse_tiles(tiles, N)).all()
+    q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("T", [64, 101])
+def test_two_rank_analysis_build(T):
+    """C3 across ranks: each rank analyses its contiguous range of tiles, one all_gather assembles [T, 3N] (even and ragged split)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_analysis_worker, args=(r, 2, port, T, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True and q.get(timeout=5) is True

@@ -241,3 +241,27 @@ def test_mosaic_dev_4to1_and_errors(ictx):
     ictx.set_library(colors)   # no tile pixels
     with pytest.raises(emo.EmosaicError, match="no tile pixels"):
         ictx.mosaic_dev(src.data_ptr(), 64, 12, 3, 0, item.data_ptr(), dist.data_ptr(), out.data_ptr())
+
+
+def test_index_at_the_tile_limit(ictx):
+    """The key holds 22 bits of tile index: T = 2^22 is the largest indexed library, T = 2^22 + 1 is scanned."""
+    rng = np.random.default_rng(22)
+    T = 1 << 22
+    colors = rng.integers(0, 256, (T + 1, 1, 3), dtype=np.uint8)
+    colors[T - 1, 0] = [1, 2, 250]        # make the last indexable tile the unique answer for one query
+    same = (colors[:T - 1, 0] == colors[T - 1, 0]).all(1)
+    colors[:T - 1][same] = [[9, 9, 9]]
+    src = rng.integers(0, 256, (24, 24, 3), dtype=np.uint8)
+    src[0, 0] = [1, 2, 250]
+    ri, rd = oracle.match(colors[:T], src)
+    ictx.set_match_mode("index")
+    ictx.set_library(colors[:T])
+    ii, id_ = ictx.match(src)
+    assert (ii == ri).all() and (id_ == rd).all()
+    assert ii[0, 0] == T and id_[0, 0] == 0
+    ictx.set_library(colors)              # one tile more: no index, the scan answers (also in "index" mode)
+    with pytest.raises(emo.EmosaicError, match="T <= 2\\^22"):
+        ictx.build_index()
+    si, sd = ictx.match(src)
+    ri2, rd2 = oracle.match(colors, src)
+    assert (si == ri2).all() and (sd == rd2).all()
