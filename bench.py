@@ -336,6 +336,32 @@ def run_ours(args):
     ctx.host_free(src_pin)
     ctx.host_free(out_pin)
 
+    # ---- context for the strong-scaling number: the same step with a whole 4096 x 4096 source per rank (weak scaling) ----
+    weak = None
+    if world > 1 and not args.no_extras:
+        item_w = torch.empty(H * W, dtype=torch.int32, device=dev)
+        dist_w = torch.empty(H * W, dtype=torch.int32, device=dev)
+        out_w = torch.empty(H * ts * W * ts * 3, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+
+        def wstep():
+            ctx.match_dev(src_d.data_ptr(), W, H, item_w.data_ptr(), dist_w.data_ptr())
+            ctx.compose_dev(item_w.data_ptr(), 0, W, H, 3, 0, out_w.data_ptr())
+
+        for _ in range(args.warmup):
+            wstep()
+        ctx.sync()
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            wstep()
+        wms = max_over_ranks(ctx.timer_stop())
+        barrier()
+        weak = {"value": world * Q_total * args.steps / (wms * 1e-3), "unit": "px/s", "ms_per_step": wms / args.steps,
+                "note": "every rank matches + composes its own full 4096x4096 source (per-GPU work fixed); not the headline"}
+        del item_w, dist_w, out_w
+        torch.cuda.empty_cache()
+
     hbm_peak, peak_src = peaks()
     c3_sharded = c3_across_ranks(ctx, torch, dist, dev, world, rank, max_over_ranks, barrier) if world > 1 and not args.no_extras else None
     line = None
@@ -394,6 +420,8 @@ def run_ours(args):
             extra.update(extras(ctx, torch, dev, hbm_peak, peak_src))
         if c3_sharded is not None:
             extra["c3_analysis_sharded"] = c3_sharded
+        if weak is not None:
+            extra["weak_scaling"] = weak
         cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
         if cpu is not None:
             extra["cpu_baseline_spread_library"] = cpu_baseline_spread(cfg)
