@@ -378,7 +378,8 @@ def run_ours(args):
             "traffic": 3240965504 if world == 1 else None,
             "peak_source": peak_src, "ms_per_launch": comp_ms, "share_of_step": comp_ms / (comp_ms + match_ms),
             "note": "achieved = (output stripe + item map + tile library once) bytes / CUDA-event time of the compose "
-                    "launch (avg over the timed steps, rank 0)",
+                    "launch (avg over the timed steps, rank 0); the peak is the measured read+write copy figure, which a "
+                    "write-mostly stream can exceed by a few per cent",
         }
         # the index lookup: 3 B of source in, 8 B of item/dist out per block, plus one gather from the L2-resident table
         look_bytes = Hs * W * 11
