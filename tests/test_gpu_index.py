@@ -265,3 +265,29 @@ def test_index_at_the_tile_limit(ictx):
     si, sd = ictx.match(src)
     ri2, rd2 = oracle.match(colors, src)
     assert (si == ri2).all() and (sd == rd2).all()
+
+
+def test_index_random_sweep(ictx):
+    """40 random (library, source) pairs — uniform, clustered, few-colour and duplicated libraries, ragged source sizes:
+    index == scan on every block, and == the oracle on every fourth case."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        T = int(rng.choice([1, 2, 3, 17, 255, 256, 257, 1000, 4999]))
+        kind = case % 4
+        if kind == 0:
+            colors = rng.integers(0, 256, (T, 1, 3), dtype=np.uint8)
+        elif kind == 1:
+            colors = np.clip(rng.normal(127, 6, (T, 1, 3)), 0, 255).astype(np.uint8)
+        elif kind == 2:
+            colors = (rng.integers(0, 3, (T, 1, 3)) * 127).astype(np.uint8)          # at most 27 distinct colours
+        else:
+            base = rng.integers(0, 256, (max(1, T // 3), 1, 3), dtype=np.uint8)
+            colors = base[rng.integers(0, base.shape[0], T)]                         # every colour ~3 times
+        H, W = int(rng.integers(1, 200)), int(rng.integers(1, 300))
+        src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ictx.set_library(colors)
+        (si, sd), (ii, id_) = both(ictx, src)
+        assert (si == ii).all() and (sd == id_).all(), f"case {case}: T={T} kind={kind} {H}x{W}"
+        if case % 4 == 0:
+            ri, rd = oracle.match(colors, src)
+            assert (ii == ri).all() and (id_ == rd).all(), f"case {case}"
