@@ -269,7 +269,7 @@ def test_index_at_the_tile_limit(ictx):
 
 def test_index_random_sweep(ictx):
     """40 random (library, source) pairs — uniform, clustered, few-colour and duplicated libraries, ragged source sizes:
-    index == scan on every block, and == the oracle on every fourth case."""
+    index == scan on every block, and == the oracle on every third case."""
     rng = np.random.default_rng(2024)
     for case in range(40):
         T = int(rng.choice([1, 2, 3, 17, 255, 256, 257, 1000, 4999]))
@@ -288,6 +288,6 @@ def test_index_random_sweep(ictx):
         ictx.set_library(colors)
         (si, sd), (ii, id_) = both(ictx, src)
         assert (si == ii).all() and (sd == id_).all(), f"case {case}: T={T} kind={kind} {H}x{W}"
-        if case % 4 == 0:
+        if case % 3 == 0:
             ri, rd = oracle.match(colors, src)
             assert (ii == ri).all() and (id_ == rd).all(), f"case {case}"
