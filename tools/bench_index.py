@@ -27,4 +27,16 @@ for T, S, kind in ((100_000, 4096, "uniform"), (100_000, 4096, "clustered"), (10
     byts = Q * 11
     print(f"T={T:8d} {kind:9s} Q={Q:10d}: build {np.median(tb):7.3f} ms (min {min(tb):.3f})  lookup {ms:7.3f} ms  "
           f"{Q/ms/1e6:8.2f} G px/s  {byts/ms/1e6:7.1f} GB/s algorithmic (3 B in + 8 B out per px)")
+    if T == 100_000 and S == 4096 and kind == "uniform":
+        # photo-like source: a smooth field (bilinear upsample of a 33x33 random grid) + N(0, sigma) noise per channel
+        for sigma in (0.0, 2.0, 8.0):
+            g = torch.rand(1, 3, 33, 33, device=dev) * 255
+            img = torch.nn.functional.interpolate(g, size=(S, S), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
+            img = (img + torch.randn_like(img) * sigma).clamp(0, 255).to(torch.uint8).contiguous().reshape(-1)
+            torch.cuda.synchronize()
+            tl = []
+            for _ in range(7):
+                ctx.timer_start(); ctx.match_dev(img.data_ptr(), S, S, item.data_ptr(), dist.data_ptr()); tl.append(ctx.timer_stop())
+            print(f"    photo-like source, noise sigma {sigma}: lookup {np.median(tl):7.3f} ms  {Q/np.median(tl)/1e6:8.2f} G px/s")
+            del img
     del src, item, dist
