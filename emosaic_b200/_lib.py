@@ -16,7 +16,7 @@ EXPORTS = [
     "emo_device_info", "emo_launch_count", "emo_timer_start", "emo_timer_stop", "emo_mark", "emo_mark_elapsed", "emo_dev_alloc", "emo_dev_free",
     "emo_host_alloc", "emo_host_free", "emo_copy_h2d", "emo_copy_d2h", "emo_analyse", "emo_analyse_dev",
     "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_build_index",
-    "emo_set_match_mode", "emo_match",
+    "emo_set_match_mode", "emo_match", "emo_topk", "emo_topk_dev",
     "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev",
     "emo_probe_int_pipe",
 ]
@@ -69,6 +69,8 @@ def load() -> C.CDLL:
         "emo_build_index": (C.c_int, [vp]),
         "emo_set_match_mode": (C.c_int, [vp, C.c_int]),
         "emo_match": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
+        "emo_topk": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32p, u32p]),
+        "emo_topk_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32p, u32p]),
         "emo_match_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
         "emo_compose": (C.c_int, [vp, i32p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_compose_dev": (C.c_int, [vp, i32p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),

@@ -204,6 +204,23 @@ class Context:
         check(self._lib.emo_match(self._h, _ptr(src), W, H, _ptr(item), _ptr(dist)))
         return item, dist
 
+    def topk(self, src, first: int, k: int):
+        """Candidates [first, first+k) of every block's list sorted by (distance, insertion rank): (item [Q,k] int32, dist
+        [Q,k] uint32), blocks row-major; past the end item 0 / dist 0xFFFFFFFF  (rendering.rs:307-321 nearest_n)."""
+        src = _u8(src)
+        if src.ndim != 3 or src.shape[2] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"src must be [H,W,3], got {src.shape}")
+        H, W = src.shape[:2]
+        d = max(self.dim, 1)
+        Q = (H // d) * (W // d)
+        item = np.zeros((Q, k), np.int32)
+        dist = np.zeros((Q, k), np.uint32)
+        check(self._lib.emo_topk(self._h, _ptr(src), W, H, first, k, _ptr(item), _ptr(dist)))
+        return item, dist
+
+    def topk_dev(self, src_dev: int, W: int, H: int, first: int, k: int, item_dev: int, dist_dev: int):
+        check(self._lib.emo_topk_dev(self._h, C.c_void_p(src_dev), W, H, first, k, C.c_void_p(item_dev), C.c_void_p(dist_dev)))
+
     def match_dev(self, src_dev: int, W: int, H: int, item_dev: int, dist_dev: int):
         check(self._lib.emo_match_dev(self._h, C.c_void_p(src_dev), W, H, C.c_void_p(item_dev), C.c_void_p(dist_dev)))
 
@@ -420,8 +437,9 @@ def render_nto1(source_img, tile_set: TileSet, tile_size: int, no_repeat: bool =
                 tint_opacity: float = 0.0, ctx: Context | None = None) -> RenderResult:
     """``render_nto1::<N>`` (rendering.rs:124-230) [+ tint block main.rs:447-478 when tint_opacity > 0]."""
     if no_repeat or randomize is not None:
-        raise EmosaicError(EMO_ERR_UNSUPPORTED, "no_repeat / randomize are order-dependent host algorithms outside the "
-                           "accelerated path (rendering.rs:163-209, :262-401)")
+        raise EmosaicError(EMO_ERR_UNSUPPORTED, "no_repeat (greedy, rayon-order dependent) / randomize (thread_rng) inside "
+                           "render_nto1 are nondeterministic host algorithms outside the accelerated path "
+                           "(rendering.rs:163-209); the deterministic no-repeat renderer is render_nto1_no_repeat")
     source_img = _u8(source_img)
     dim = _isqrt_exact(tile_set.N)
     H, W = source_img.shape[:2]
@@ -434,6 +452,66 @@ def render_nto1(source_img, tile_set: TileSet, tile_size: int, no_repeat: bool =
         image, item, dist = ctx.mosaic(source_img, 4, tint_alpha(tint_opacity))
     else:
         image, item, dist = ctx.mosaic(source_img, 3, 0)
+    return RenderResult(image, tile_set, item, dist)
+
+
+def render_nto1_no_repeat(source_img, tile_set: TileSet, tile_size: int, ctx: Context | None = None, page: int = 64) -> RenderResult:
+    """``render_nto1_no_repeat::<N>`` (rendering.rs:262-401): every block gets the nearest tile that no nearer block has
+    taken; a tile is used once, in either orientation.  The ranked candidate lists (the reference's Scoring phase,
+    nearest_n(100000) per block, :307-321) come from the GPU in pages (emo_topk); the greedy merge (:341-392) runs here:
+    blocks ordered by the distance of their best remaining candidate — ties by the reference's block number
+    n = bx * vtiles + by (:300-301), the canonical order of DESIGN.md — a block whose candidate is taken moves on to its
+    next one; a block that runs out of candidates stays black (:347-351).  The image is composed on the GPU."""
+    import heapq
+
+    source_img = _u8(source_img)
+    dim = _isqrt_exact(tile_set.N)
+    H, W = source_img.shape[:2]
+    if W % dim or H % dim:
+        raise EmosaicError(EMO_ERR_ARG, f"Invalid source dimensions ({W}x{H}): Dimensions must be divisible by {dim}")
+    if tile_size % dim:
+        raise EmosaicError(EMO_ERR_ARG, f"Invalid tile size: Tile size must be divisible by {dim}")
+    bh, bw = H // dim, W // dim
+    T = len(tile_set)
+    if bh * bw > 2 * T:  # rendering.rs:292-298
+        raise EmosaicError(EMO_ERR_ARG, f"Insufficient tiles for no-repeat mode: need {bh * bw} tiles but only have {2 * T} available")
+    ctx = tile_set.build_kiddo(ctx, tile_size)
+    L = T if tile_set.N == 1 else 2 * T          # candidates per list (the N = 1 mirror twins are never reached)
+    k0 = max(1, min(page, L, 1024))
+    items, dists = ctx.topk(source_img, 0, k0)
+    lists = [(items[q], dists[q], 0) for q in range(bh * bw)]   # (items, dists, position of lists[q][0] in the full list)
+    ptr = [0] * (bh * bw)                                        # position in the full list
+    heap = [(int(dists[by * bw + bx, 0]), bx * bh + by, by * bw + bx) for by in range(bh) for bx in range(bw)]
+    heapq.heapify(heap)
+    item = np.zeros(bh * bw, np.int32)
+    dist = np.zeros(bh * bw, np.uint32)
+    used = set()
+    while heap:
+        d, n, q = heapq.heappop(heap)
+        its, ds, first = lists[q]
+        it = int(its[ptr[q] - first])
+        if abs(it) not in used:
+            used.add(abs(it))
+            item[q], dist[q] = it, d
+            continue
+        ptr[q] += 1
+        if ptr[q] >= L:
+            continue                                             # out of candidates: the block stays black
+        if ptr[q] - first >= len(its):                           # next page of this block's list (compute_nearest refill, :384-386)
+            by, bx = divmod(q, bw)
+            blk = np.ascontiguousarray(source_img[by * dim:(by + 1) * dim, bx * dim:(bx + 1) * dim])
+            k = max(1, min(2 * len(its), L - ptr[q], 1024))
+            pi, pd = ctx.topk(blk, ptr[q], k)
+            its, ds, first = pi[0], pd[0], ptr[q]
+            lists[q] = (its, ds, first)
+        heapq.heappush(heap, (int(ds[ptr[q] - first]), n, q))
+    item = item.reshape(bh, bw)
+    dist = dist.reshape(bh, bw)
+    placed = item != 0
+    image = ctx.compose(np.where(placed, item, 1).astype(np.int32))
+    if not placed.all():                                         # RgbImage::new: unplaced blocks stay black
+        mask = np.repeat(np.repeat(~placed, tile_size, 0), tile_size, 1)
+        image[mask] = 0
     return RenderResult(image, tile_set, item, dist)
 
 

@@ -433,6 +433,44 @@ int emo_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t 
     return EMO_OK;
 }
 
+// ---- ranked candidate lists (no-repeat) -----------------------------------------------------------------------------
+static int check_topk_args(emo_ctx *ctx, const void *src, uint32_t W, uint32_t H, uint32_t k, const void *item, const void *dist) {
+    int rc = check_match_args(ctx, src, W, H);
+    if (rc) return rc;
+    EMO_REQUIRE(item && dist, EMO_ERR_ARG, "topk: item/dist is NULL");
+    EMO_REQUIRE(k >= 1 && k <= 1024, EMO_ERR_ARG, "topk: k=%u outside [1,1024]", k);
+    if (ctx->wide) {
+        emo_set_error("topk: ranked lists exist for --mode 1..4 (N = 1, 4, 9, 16), not N=%u", ctx->N);
+        return EMO_ERR_UNSUPPORTED;
+    }
+    return EMO_OK;
+}
+
+int emo_topk_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, int32_t *item, uint32_t *dist) {
+    int rc = check_topk_args(ctx, src, W, H, k, item, dist);
+    if (rc) return rc;
+    EMO_REQUIRE((uintptr_t)item % 4 == 0 && (uintptr_t)dist % 4 == 0, EMO_ERR_ARG, "topk: item/dist must be 4-byte aligned");
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_topk(ctx, src, W, H, first, k, item, dist);
+}
+
+int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, int32_t *item, uint32_t *dist) {
+    int rc = check_topk_args(ctx, src, W, H, k, item, dist);
+    if (rc) return rc;
+    EMO_CK(cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)W * H * 3, ob = (size_t)(W / ctx->dim) * (H / ctx->dim) * k * 4;
+    if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], sb))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], ob))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[4], &ctx->stage_cap[4], ob))) return rc;
+    EMO_CK(cudaMemcpyAsync(ctx->stage[2], src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = emo_launch_topk(ctx, (const uint8_t *)ctx->stage[2], W, H, first, k, (int32_t *)ctx->stage[3], (uint32_t *)ctx->stage[4])))
+        return rc;
+    EMO_CK(cudaMemcpyAsync(item, ctx->stage[3], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaMemcpyAsync(dist, ctx->stage[4], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
 static int check_compose_args(emo_ctx *ctx, const void *item, const void *src, uint32_t W, uint32_t H, uint32_t oc,
                               const void *out) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "compose: ctx is NULL");

@@ -131,6 +131,23 @@ int emo_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t 
 int emo_match_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, int32_t *item_dev,
                   uint32_t *dist_dev);
 
+/* ---- (3b) ranked candidates for the no-repeat renderer --------------------------------------
+ * Replaces the Scoring phase of render_nto1_no_repeat (src/mosaic/rendering.rs:307-321,
+ * nearest_n::<Manhattan>(coords, 100000) per block, and the refill compute_nearest(n, 10) at
+ * :384-386).  For every dim x dim block of src: the candidates at positions [first, first + k) of
+ * the block's candidate list sorted by (L1 distance, insertion rank) — rank 2t = tile t, 2t + 1 =
+ * its mirror (tileset.rs:178-190; the order among equal distances is this library's canonical
+ * one).  item_out/dist_out are [H/dim * W/dim][k], blocks row-major (by * bw + bx);
+ * positions past the end of the list hold item 0 / dist 0xFFFFFFFF.  1 <= k <= 1024.
+ * N = 1, 4, 9, 16 (--mode 1..4); EMO_ERR_UNSUPPORTED otherwise.  For N == 1 the mirrored twin of a
+ * tile (same vector, directly behind it in every list) is omitted: using a tile retires both
+ * orientations (rendering.rs:357-358).  The greedy assignment that consumes the lists
+ * (rendering.rs:341-392) is sequential and lives in the host layers (render_nto1_no_repeat). */
+int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k,
+             int32_t *item_out, uint32_t *dist_out);
+int emo_topk_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, uint32_t first, uint32_t k,
+                 int32_t *item_out_dev, uint32_t *dist_out_dev);
+
 /* ---- (4) compose (+tint) -----------------------------------------------------------------
  * Replaces render() (src/mosaic/rendering.rs:51-101) + TileSet::get_image()
  * (tiles/tileset.rs:146-161) and, when out_channels == 4, the tint block

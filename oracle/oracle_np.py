@@ -127,3 +127,107 @@ def l1_voronoi_table(colors: np.ndarray, bits: int = 8):
         for i in range(S - 2, -1, -1):
             a[i] = np.minimum(a[i], a[i + 1] + INC)
     return lut & (INC - 1), lut >> 22
+
+
+# ---- no-repeat renderer (rendering.rs:262-401) ---------------------------------------------------------------
+def sorted_candidates(colors: np.ndarray, src: np.ndarray):
+    """nearest_n::<Manhattan>(coords, 100000) for every block (rendering.rs:307-321): ALL candidates of the search set
+    (tileset.rs:178-190: +idx then -idx per tile), nearest first.  Canonical order inside equal distances: insertion
+    rank (2t = tile t, 2t+1 = its mirror) — kiddo's own order among equal distances is unpinned.
+    Returns (item [Q, 2T] int32 signed 1-based, dist [Q, 2T] int64), blocks in row-major order (by * bw + bx)."""
+    T, N = colors.shape[:2]
+    base = colors.reshape(T, 3 * N)
+    cand = np.empty((2 * T, 3 * N), np.int64)
+    cand[0::2] = base
+    cand[1::2] = mirror(base, N)
+    q = queries(src, N).astype(np.int64).reshape(-1, 3 * N)
+    d = np.abs(q[:, None, :] - cand[None, :, :]).sum(axis=2)
+    order = np.argsort(d, axis=1, kind="stable")                      # stable: ties stay in rank order
+    rank_item = np.where(np.arange(2 * T) % 2 == 0, np.arange(2 * T) // 2 + 1, -(np.arange(2 * T) // 2 + 1)).astype(np.int32)
+    return rank_item[order], np.take_along_axis(d, order, axis=1)
+
+
+def no_repeat_assign(colors: np.ndarray, src: np.ndarray, report_ties: bool = False):
+    """render_nto1_no_repeat (rendering.rs:262-401) up to the placement of tiles: every block gets the nearest tile
+    nobody nearer has taken; a tile is used once, in either orientation (`used.insert(item); used.insert(-item)`,
+    :357-358).  The reference keeps the blocks in a vector sorted by the distance of their current best candidate
+    (:323-326), pops the smallest, and re-inserts a block whose candidate was taken under its next candidate's
+    distance (:380-391) — a merge of the per-block sorted lists in globally increasing distance.  Order among equal
+    distances (its unstable sort and `insert(ix + 1)`) is unpinned; canonical here: (distance, n) with the reference's
+    block number n = bx * vtiles + by (:300-301).  Blocks that run out of candidates stay unplaced (item 0; :347-351).
+    Returns (item [bh,bw] int32, dist [bh,bw] uint32) (+ whether two blocks ever competed at equal distance, i.e.
+    whether the canonical order was needed, if report_ties)."""
+    import heapq
+
+    T, N = colors.shape[:2]
+    dim = int(np.sqrt(N))
+    bh, bw = src.shape[0] // dim, src.shape[1] // dim
+    if bh * bw > 2 * T:
+        raise AssertionError(f"Insufficient tiles for no-repeat mode: need {bh * bw} tiles but only have {2 * T} available")
+    items, dists = sorted_candidates(colors, src)
+    item = np.zeros(bh * bw, np.int32)
+    dist = np.zeros(bh * bw, np.uint32)
+    ptr = np.zeros(bh * bw, np.int64)
+    heap = []
+    for by in range(bh):
+        for bx in range(bw):
+            q = by * bw + bx
+            heap.append((int(dists[q, 0]), bx * bh + by, q))
+    heapq.heapify(heap)
+    used = set()
+    ties = False
+    while heap:
+        d, n, q = heapq.heappop(heap)
+        ties = ties or (bool(heap) and heap[0][0] == d)
+        it = int(items[q, ptr[q]])
+        if abs(it) not in used:
+            used.add(abs(it))
+            item[q], dist[q] = it, d
+            continue
+        ptr[q] += 1
+        if ptr[q] < items.shape[1]:
+            heapq.heappush(heap, (int(dists[q, ptr[q]]), n, q))
+    if report_ties:
+        return item.reshape(bh, bw), dist.reshape(bh, bw), ties
+    return item.reshape(bh, bw), dist.reshape(bh, bw)
+
+
+def no_repeat_assign_literal(colors: np.ndarray, src: np.ndarray):
+    """The same function written the way the reference writes it — a vector of (n, remaining candidates) kept sorted by the
+    distance of each block's best remaining candidate, popped from the end, re-inserted by binary search — to check
+    that the heap formulation above is the same algorithm.  Only defined for inputs without equal distances between
+    different (block, candidate) pairs at decision points (the reference's tie order is implementation-defined);
+    small inputs only (pure Python)."""
+    import bisect
+
+    T, N = colors.shape[:2]
+    dim = int(np.sqrt(N))
+    bh, bw = src.shape[0] // dim, src.shape[1] // dim
+    items, dists = sorted_candidates(colors, src)
+    matches = []
+    for n in range(bw * bh):                                         # :317-321, n -> (x = n / vtiles, y = n % vtiles)
+        bx, by = n // bh, n % bh
+        q = by * bw + bx
+        near = [(int(dists[q, j]), int(items[q, j])) for j in range(items.shape[1])]
+        near.reverse()                                               # :312 nearest.reverse(): best candidate last
+        matches.append((n, near))
+    matches.sort(key=lambda m: -m[1][-1][0])                         # :323-326 descending, popped from the end
+    item = np.zeros((bh, bw), np.int32)
+    dist = np.zeros((bh, bw), np.uint32)
+    used = set()
+    while matches:
+        n, near = matches.pop()
+        if not near:
+            continue
+        d, it = near.pop()
+        bx, by = n // bh, n % bh
+        if it not in used:
+            used.add(it)
+            used.add(-it)
+            item[by, bx], dist[by, bx] = it, d
+        else:
+            if not near:
+                continue
+            keys = [-m[1][-1][0] for m in matches]                   # ascending view of the descending vector
+            matches.insert(bisect.bisect_right(keys, -near[-1][0]), (n, near))
+    return item, dist
