@@ -8,7 +8,8 @@ Mirrors src/main.rs:28-138 (flags), :542-667 (n_to_1: dimension rule, cache, ren
 Decoding, resizing and directory walking stay on the host (PIL) and outside the accelerated path; tile
 preparation here is decode -> EXIF transpose -> optional centre-square crop -> Lanczos resize (the reference's
 white-border trimming and its ~/.cache/mosaic JPEG cache are host stages that are not reproduced).
---no-repeat / --randomize / --greedy / --html / --web are rejected: outside the accelerated path.
+--no-repeat runs the no-repeat renderer (rendering.rs:262-401); --randomize / --greedy / --html / --web are rejected:
+outside the accelerated path.
 """
 from __future__ import annotations
 
@@ -114,8 +115,10 @@ def main(argv=None) -> int:
     if not (0.0 <= args.tint_opacity <= 1.0):
         print("error: Value must be between 0 and 1", file=sys.stderr)
         return 2
-    if args.no_repeat or args.randomize is not None or args.greedy or args.html or args.web:
-        print("error: --no-repeat/--randomize/--greedy/--html/--web are outside the accelerated path", file=sys.stderr)
+    if args.randomize is not None or args.greedy or args.html or args.web:
+        # main.rs:663-667: --no-repeat alone is render_nto1_no_repeat (supported); with --greedy, or with --randomize,
+        # it is render_nto1's rayon-order / thread_rng dependent branch
+        print("error: --randomize/--greedy/--html/--web are outside the accelerated path", file=sys.stderr)
         return 2
     if not os.path.isdir(args.tiles_dir):
         print(f"error: tiles directory {args.tiles_dir} does not exist", file=sys.stderr)
@@ -173,9 +176,21 @@ def main(argv=None) -> int:
         if len(paths) == 0:
             print("error: no tiles", file=sys.stderr)
             return 1
-        ctx.set_library(colors, px)
-        out, item, dist = ctx.mosaic(img, 3, 0)
-        stats.summarise(item, dist, paths)
+        if args.no_repeat:  # main.rs:663-664
+            try:
+                res = api.render_nto1_no_repeat(img, api.TileSet.from_arrays(colors, px, paths, dates), ts, ctx)
+            except api.EmosaicError as e:
+                print(f"error: {e}", file=sys.stderr)
+                return 1
+            out, item, dist = res.image, res.item, res.dist
+            if args.tint_opacity > 0.0 and (item == 0).any():
+                print("error: --tint-opacity with unplaced blocks (fewer tiles than blocks) is not supported", file=sys.stderr)
+                return 1
+        else:
+            ctx.set_library(colors, px)
+            out, item, dist = ctx.mosaic(img, 3, 0)
+        placed = item != 0  # the reference records statistics for placed tiles only (rendering.rs:362-365)
+        stats.summarise(item[placed], dist[placed], paths)
         src_for_tint = original  # main.rs:447-466 overlays the image as opened, not the copy resized for matching
 
     if args.tint_opacity > 0.0:  # main.rs:447-478: RGBA PNG, early return (no stats image)

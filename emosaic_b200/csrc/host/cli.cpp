@@ -39,7 +39,7 @@ static void find_images(const std::string &dir, const std::vector<std::string> &
 int main(int argc, char **argv) {
     uint32_t tile_size = 16;
     std::string output = "./output.jpg", img_path, tiles_dir, mode = "1";
-    bool crop = false, force = false, mosaic = false;
+    bool crop = false, force = false, mosaic = false, no_repeat = false;
     double tint = 0.0;
     std::vector<std::string> exts = {"jpg", "jpeg"}, pos;
     for (int i = 1; i < argc; i++) {
@@ -52,7 +52,8 @@ int main(int argc, char **argv) {
         else if (a == "-f" || a == "--force") force = true;
         else if (a == "-t" || a == "--tint-opacity") tint = std::stod(next());
         else if (a == "--extensions") { exts.clear(); while (i + 1 < argc && argv[i + 1][0] != '-') exts.push_back(argv[++i]); }
-        else if (a == "--no-repeat" || a == "--randomize" || a == "--greedy" || a == "--html" || a == "--web") {
+        else if (a == "--no-repeat") no_repeat = true;  // main.rs:663-664: render_nto1_no_repeat
+        else if (a == "--randomize" || a == "--greedy" || a == "--html" || a == "--web") {
             fprintf(stderr, "error: %s is outside the accelerated path\n", a.c_str());
             return 2;
         } else if (a == "mosaic") mosaic = true;
@@ -113,7 +114,9 @@ int main(int argc, char **argv) {
             std::ofstream(cache_path, std::ios::binary).write((const char *)blob.data(), blob.size());
         }
         fprintf(stderr, "Tile set with %zu tiles\n", ts.len());
-        RenderResult r = render_nto1(ctx, original, ts, tile_size, false, std::nullopt, tint);
+        if (no_repeat && tint > 0.0) throw Error(EMO_ERR_UNSUPPORTED, "--no-repeat with --tint-opacity is not wired in this front end");
+        RenderResult r = no_repeat ? render_nto1_no_repeat(ctx, original, ts, tile_size)
+                                   : render_nto1(ctx, original, ts, tile_size, false, std::nullopt, tint);
         if (tint > 0.0) {  // main.rs:447-478: RGBA PNG, early return
             write_png(output, r.image);
             return 0;

@@ -1,6 +1,10 @@
 // emosaic.cpp — see emosaic.hpp.  Host glue only; every pixel/index comes out of libemosaic_cuda.so.
 #include "emosaic.hpp"
 
+#include <tuple>
+
+#include <queue>
+
 #include <zlib.h>
 
 #include <algorithm>
@@ -133,7 +137,9 @@ uint8_t tint_alpha(double t) {
 RenderResult render_nto1(Context &ctx, const Image &source, const TileSet &tile_set, uint32_t tile_size, bool no_repeat,
                          std::optional<double> randomize, double tint_opacity) {
     if (no_repeat || randomize)
-        throw Error(EMO_ERR_UNSUPPORTED, "no_repeat / randomize are order-dependent host algorithms outside the accelerated path");
+        throw Error(EMO_ERR_UNSUPPORTED,
+                    "no_repeat (greedy, rayon-order dependent) / randomize (thread_rng) inside render_nto1 are outside the accelerated "
+                    "path; the deterministic no-repeat renderer is render_nto1_no_repeat");
     const uint32_t dim = isqrt_exact(tile_set.cells());
     if (source.channels != 3) throw Error(EMO_ERR_ARG, "render_nto1: RGB source expected");
     if (source.width % dim || source.height % dim)  // main.rs:603-611
@@ -150,6 +156,93 @@ RenderResult render_nto1(Context &ctx, const Image &source, const TileSet &tile_
     r.dist.resize((size_t)r.bw * r.bh);
     check(emo_mosaic(ctx.handle(), source.data.data(), source.width, source.height, oc, tint_alpha(tint_opacity), r.item.data(),
                      r.dist.data(), r.image.data.data()));
+    return r;
+}
+
+// rendering.rs:262-401.  The ranked candidate lists (Scoring phase, :307-321) come from the GPU in pages (emo_topk); the
+// greedy merge (:341-392) runs here: blocks ordered by the distance of their best remaining candidate, ties by the
+// reference's block number n = bx * vtiles + by (:300-301; the canonical order), a block whose candidate is taken
+// moves on to its next one, a block that runs out of candidates stays black (:347-351).
+RenderResult render_nto1_no_repeat(Context &ctx, const Image &source, const TileSet &tile_set, uint32_t tile_size, uint32_t page) {
+    const uint32_t dim = isqrt_exact(tile_set.cells());
+    if (source.channels != 3) throw Error(EMO_ERR_ARG, "render_nto1_no_repeat: RGB source expected");
+    if (source.width % dim || source.height % dim)
+        throw Error(EMO_ERR_ARG, "Invalid source dimensions (" + std::to_string(source.width) + "x" + std::to_string(source.height) +
+                                     "): Dimensions must be divisible by " + std::to_string(dim));
+    if (tile_size % dim) throw Error(EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by " + std::to_string(dim));
+    const uint32_t bw = source.width / dim, bh = source.height / dim;
+    const size_t Q = (size_t)bw * bh, T = tile_set.len();
+    if (Q > 2 * T)  // rendering.rs:292-298
+        throw Error(EMO_ERR_ARG, "Insufficient tiles for no-repeat mode: need " + std::to_string(Q) + " tiles but only have " +
+                                     std::to_string(2 * T) + " available");
+    tile_set.build_kiddo(ctx, tile_size);
+    const size_t L = tile_set.cells() == 1 ? T : 2 * T;  // the N = 1 mirror twins are never reached
+    struct List {
+        std::vector<int32_t> item;
+        std::vector<uint32_t> dist;
+        size_t first = 0;  // position of item[0] in the block's full list
+    };
+    const uint32_t k0 = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)page, L, (size_t)1024}));
+    std::vector<int32_t> pi(Q * k0);
+    std::vector<uint32_t> pd(Q * k0);
+    check(emo_topk(ctx.handle(), source.data.data(), source.width, source.height, 0, k0, pi.data(), pd.data()));
+    std::vector<List> lists(Q);
+    std::vector<size_t> ptr(Q, 0);
+    using Entry = std::tuple<uint32_t, uint32_t, uint32_t>;  // (distance, n, block)
+    std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry>> heap;
+    for (uint32_t by = 0; by < bh; by++)
+        for (uint32_t bx = 0; bx < bw; bx++) {
+            const size_t q = (size_t)by * bw + bx;
+            lists[q].item.assign(pi.begin() + q * k0, pi.begin() + (q + 1) * k0);
+            lists[q].dist.assign(pd.begin() + q * k0, pd.begin() + (q + 1) * k0);
+            heap.emplace(lists[q].dist[0], bx * bh + by, (uint32_t)q);
+        }
+    RenderResult r;
+    r.bw = bw;
+    r.bh = bh;
+    r.item.assign(Q, 0);
+    r.dist.assign(Q, 0);
+    std::vector<bool> used(T + 1, false);
+    std::vector<uint8_t> blk((size_t)dim * dim * 3);
+    while (!heap.empty()) {
+        auto [d, n, q] = heap.top();
+        heap.pop();
+        List &l = lists[q];
+        const int32_t it = l.item[ptr[q] - l.first];
+        const size_t a = (size_t)(it < 0 ? -it : it);
+        if (!used[a]) {
+            used[a] = true;
+            r.item[q] = it;
+            r.dist[q] = d;
+            continue;
+        }
+        if (++ptr[q] >= L) continue;  // out of candidates: stays black
+        if (ptr[q] - l.first >= l.item.size()) {  // next page of this block's list (compute_nearest refill, :384-386)
+            const uint32_t by = q / bw, bx = q % bw;
+            for (uint32_t row = 0; row < dim; row++)
+                std::memcpy(&blk[(size_t)row * dim * 3], source.pixel(bx * dim, by * dim + row), (size_t)dim * 3);
+            const uint32_t k = (uint32_t)std::max<size_t>(1, std::min<size_t>({2 * l.item.size(), L - ptr[q], (size_t)1024}));
+            l.item.resize(k);
+            l.dist.resize(k);
+            l.first = ptr[q];
+            check(emo_topk(ctx.handle(), blk.data(), dim, dim, (uint32_t)ptr[q], k, l.item.data(), l.dist.data()));
+        }
+        heap.emplace(l.dist[ptr[q] - l.first], n, q);
+    }
+    std::vector<int32_t> placed(r.item);
+    bool holes = false;
+    for (auto &v : placed)
+        if (v == 0) {
+            v = 1;
+            holes = true;
+        }
+    r.image = Image(bw * tile_size, bh * tile_size, 3);
+    check(emo_compose(ctx.handle(), placed.data(), nullptr, source.width, source.height, 3, 0, r.image.data.data()));
+    if (holes)  // RgbImage::new: unplaced blocks stay black
+        for (size_t q = 0; q < Q; q++)
+            if (r.item[q] == 0)
+                for (uint32_t y = 0; y < tile_size; y++)
+                    std::memset(r.image.pixel((uint32_t)(q % bw) * tile_size, (uint32_t)(q / bw) * tile_size + y), 0, (size_t)tile_size * 3);
     return r;
 }
 

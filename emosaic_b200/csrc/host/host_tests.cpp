@@ -197,7 +197,21 @@ int main(int argc, char **argv) {
                 CHECK(r.image == img);
                 CHECK(r.dist[0] == 0 && r.dist[1] == 0);
             }
-            CHECK(throws_with([&] { render_nto1(ctx, uni[0], ts, dim, true); }, "outside the accelerated path"));
+            CHECK(throws_with([&] { render_nto1(ctx, uni[0], ts, dim, true); }, "outside the accelerated"));
+            // mod.rs:122-126 and :140-144: the same round trips through render_nto1_no_repeat
+            shown = 0;
+            for (const Image &img : uni) {
+                CHECK(render_nto1_no_repeat(ctx, img, ts, dim).image == img);
+                if (++shown >= 32) break;
+            }
+            for (size_t a = 0; a + 1 < uni.size() && a < 32; a += 2) {
+                Image img(dim, 2 * dim, 3);
+                memcpy(img.data.data(), uni[a].data.data(), uni[a].data.size());
+                memcpy(img.data.data() + uni[a].data.size(), uni[a + 1].data.data(), uni[a + 1].data.size());
+                RenderResult r = render_nto1_no_repeat(ctx, img, ts, dim, 1);  // one candidate per page: every conflict refills
+                CHECK(r.image == img);
+                CHECK(r.item[0] != r.item[1] && r.item[0] != -r.item[1]);
+            }
         });
     }
     // the 1to1 search index answers exactly like the scan (include/emosaic_cuda.h §2b)
@@ -223,6 +237,20 @@ int main(int argc, char **argv) {
         four.push_tile_with_image("", std::vector<uint8_t>(12, 0), Image(8, 8, 3));
         four.build_kiddo(ctx, 8);
         CHECK(throws_with([&] { ctx.build_index(); }, "N == 1"));
+    });
+    // rendering.rs:292-298 and :347-351
+    run("test_no_repeat_rules", [&] {
+        TileSet ts(1);
+        for (int i = 0; i < 3; i++) {
+            Image tile(4, 4, 3);
+            for (auto &v : tile.data) v = (uint8_t)(i * 100);
+            ts.push_tile_with_image("", {(uint8_t)(i * 100), (uint8_t)(i * 100), (uint8_t)(i * 100)}, tile);
+        }
+        CHECK(throws_with([&] { render_nto1_no_repeat(ctx, Image(7, 1, 3), ts, 4); }, "Insufficient tiles for no-repeat mode: need 7 tiles but only have 6"));
+        RenderResult r = render_nto1_no_repeat(ctx, Image(5, 1, 3), ts, 4);  // 5 black blocks, 3 tiles: two blocks stay unplaced
+        int placed = 0;
+        for (int32_t it : r.item) placed += it != 0;
+        CHECK(placed == 3 && r.item[0] == 1 && r.dist[0] == 0);
     });
     // main.rs:603-615 exits become errors
     run("test_dimension_rules", [&] {

@@ -89,7 +89,9 @@ def test_cli_tint_and_random(workdir):
 def test_cli_rejects(workdir):
     d, _ = workdir
     base = ["-s", "8", str(d / "src.png"), "mosaic", str(d / "tiles")]
-    assert cli.main(base + ["--no-repeat"]) == 2
+    assert cli.main(base + ["--no-repeat", "--greedy"]) == 2     # render_nto1's rayon-order dependent branch (main.rs:663-667)
+    assert cli.main(base + ["--randomize", "5"]) == 2
+    assert cli.main(base + ["--no-repeat"]) == 1                  # 36 x 48 blocks for 60 tiles: "Insufficient tiles"
     assert cli.main(["-s", "9", str(d / "src.png"), "mosaic", str(d / "tiles"), "-m", "2"]) == 1  # tile size % dim
     assert cli.main(["-s", "8", str(d / "src.png"), "mosaic", str(d / "nope")]) == 1
     assert cli.main(["-s", "0", str(d / "src.png"), "mosaic", str(d / "tiles")]) == 1      # main.rs:272-283
@@ -116,3 +118,18 @@ def test_cli_tint_uses_original_image_as_overlay(workdir):
     want = oracle.tint(oracle.render(px, item), src, 127)
     got = np.asarray(PIL.open(out))
     assert got.shape == (nh * ts, nw * ts, 4) and (got == want).all()
+
+
+def test_cli_no_repeat(workdir):
+    """--no-repeat (main.rs:663-664 -> render_nto1_no_repeat): a 6 x 8 block source for the 60 tiles; every tile at most once."""
+    from oracle import oracle_np as onp
+    d, src = workdir
+    ts = 12
+    small = src[:12, :16]
+    PIL.fromarray(small).save(d / "small.png")
+    out = d / "out_nr.png"
+    assert cli.main(["-s", str(ts), "-o", str(out), str(d / "small.png"), "mosaic", str(d / "tiles"), "-m", "2", "--no-repeat", "-f"]) == 0
+    paths, colors, _, _, px_an, px_rd = expected(d / "tiles", small, 2, ts, False)
+    item, dist = onp.no_repeat_assign(colors, small)
+    assert (np.asarray(PIL.open(out)) == oracle.render(px_rd, item)).all()
+    assert len(set(np.abs(item).reshape(-1).tolist())) == item.size

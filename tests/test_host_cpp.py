@@ -69,8 +69,23 @@ def test_cpp_cli_end_to_end(tmp_path):
         assert r.returncode == 0 and "Reusing analysis cache" in r.stderr, r.stderr
         got = np.asarray(PIL.open(out))
         assert got.shape[2] == 4 and (got == oracle.tint(oracle.render(px, item), src, 127)).all()
-    r = subprocess.run([exe, "-s", "8", str(tmp_path / "src.png"), "mosaic", str(tiles_dir), "--no-repeat"], capture_output=True, text=True)
+    r = subprocess.run([exe, "-s", "8", str(tmp_path / "src.png"), "mosaic", str(tiles_dir), "--greedy"], capture_output=True, text=True)
     assert r.returncode == 2
+    # --no-repeat (main.rs:663-664): 560 blocks for 50 tiles is refused, a 6 x 8 block source gets every tile at most once
+    base = [exe, "-s", str(ts), "-o", str(tmp_path / "nr.png"), "mosaic", str(tiles_dir), "-m", "1", "--extensions", "png", "--no-repeat"]
+    r = subprocess.run(base[:5] + [str(tmp_path / "src.png")] + base[5:], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Insufficient tiles for no-repeat mode: need 560 tiles but only have 100" in r.stderr
+    from oracle import oracle_np as onp
+    small = src[:6, :8]
+    PIL.fromarray(small).save(tmp_path / "small.png")
+    r = subprocess.run(base[:5] + [str(tmp_path / "small.png")] + base[5:], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    found = _find_images(str(tiles_dir))
+    px = np.stack([tiles[paths.index(p)] for p in found])
+    colors = oracle.analyse_tiles(px, 1)
+    item, dist = onp.no_repeat_assign(colors, small)
+    assert (np.asarray(PIL.open(tmp_path / "nr.png")) == oracle.render(px, item)).all()
+    assert len(set(np.abs(item).reshape(-1).tolist())) == 48
 
 
 def _find_images(root):
