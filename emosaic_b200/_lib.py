@@ -69,8 +69,8 @@ def load() -> C.CDLL:
         "emo_build_index": (C.c_int, [vp]),
         "emo_set_match_mode": (C.c_int, [vp, C.c_int]),
         "emo_match": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
-        "emo_topk": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32p, u32p]),
-        "emo_topk_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32p, u32p]),
+        "emo_topk": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, i32p, u32p]),
+        "emo_topk_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, i32p, u32p]),
         "emo_match_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
         "emo_compose": (C.c_int, [vp, i32p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_compose_dev": (C.c_int, [vp, i32p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),

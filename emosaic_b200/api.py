@@ -204,9 +204,10 @@ class Context:
         check(self._lib.emo_match(self._h, _ptr(src), W, H, _ptr(item), _ptr(dist)))
         return item, dist
 
-    def topk(self, src, first: int, k: int):
+    def topk(self, src, first: int, k: int, exclude=None):
         """Candidates [first, first+k) of every block's list sorted by (distance, insertion rank): (item [Q,k] int32, dist
-        [Q,k] uint32), blocks row-major; past the end item 0 / dist 0xFFFFFFFF  (rendering.rs:307-321 nearest_n)."""
+        [Q,k] uint32), blocks row-major; past the end item 0 / dist 0xFFFFFFFF  (rendering.rs:307-321 nearest_n).
+        exclude: optional [T] uint8, 1 = tile retired (left out of every list, rendering.rs:366-380)."""
         src = _u8(src)
         if src.ndim != 3 or src.shape[2] != 3:
             raise EmosaicError(EMO_ERR_ARG, f"src must be [H,W,3], got {src.shape}")
@@ -215,11 +216,16 @@ class Context:
         Q = (H // d) * (W // d)
         item = np.zeros((Q, k), np.int32)
         dist = np.zeros((Q, k), np.uint32)
-        check(self._lib.emo_topk(self._h, _ptr(src), W, H, first, k, _ptr(item), _ptr(dist)))
+        if exclude is not None:
+            exclude = _u8(exclude).reshape(-1)
+            if exclude.size != self.T:
+                raise EmosaicError(EMO_ERR_ARG, f"exclude must have one byte per tile ({self.T}), got {exclude.size}")
+        check(self._lib.emo_topk(self._h, _ptr(src), W, H, first, k, _ptr(exclude), _ptr(item), _ptr(dist)))
         return item, dist
 
-    def topk_dev(self, src_dev: int, W: int, H: int, first: int, k: int, item_dev: int, dist_dev: int):
-        check(self._lib.emo_topk_dev(self._h, C.c_void_p(src_dev), W, H, first, k, C.c_void_p(item_dev), C.c_void_p(dist_dev)))
+    def topk_dev(self, src_dev: int, W: int, H: int, first: int, k: int, item_dev: int, dist_dev: int, exclude_dev: int = 0):
+        check(self._lib.emo_topk_dev(self._h, C.c_void_p(src_dev), W, H, first, k, C.c_void_p(exclude_dev or 0), C.c_void_p(item_dev),
+                                     C.c_void_p(dist_dev)))
 
     def match_dev(self, src_dev: int, W: int, H: int, item_dev: int, dist_dev: int):
         check(self._lib.emo_match_dev(self._h, C.c_void_p(src_dev), W, H, C.c_void_p(item_dev), C.c_void_p(dist_dev)))
@@ -477,10 +483,11 @@ def render_nto1_no_repeat(source_img, tile_set: TileSet, tile_size: int, ctx: Co
         raise EmosaicError(EMO_ERR_ARG, f"Insufficient tiles for no-repeat mode: need {bh * bw} tiles but only have {2 * T} available")
     ctx = tile_set.build_kiddo(ctx, tile_size)
     L = T if tile_set.N == 1 else 2 * T          # candidates per list (the N = 1 mirror twins are never reached)
-    k0 = max(1, min(page, L, 1024))
+    k0 = max(1, min(page, 1024))
     items, dists = ctx.topk(source_img, 0, k0)
-    lists = [(items[q], dists[q], 0) for q in range(bh * bw)]   # (items, dists, position of lists[q][0] in the full list)
-    ptr = [0] * (bh * bw)                                        # position in the full list
+    lists = [(items[q], dists[q]) for q in range(bh * bw)]      # current page of every block
+    ptr = [0] * (bh * bw)                                        # position inside the page
+    retired = np.zeros(T, np.uint8)                              # tiles placed so far (what the reference removes from the tree)
     heap = [(int(dists[by * bw + bx, 0]), bx * bh + by, by * bw + bx) for by in range(bh) for bx in range(bw)]
     heapq.heapify(heap)
     item = np.zeros(bh * bw, np.int32)
@@ -488,23 +495,30 @@ def render_nto1_no_repeat(source_img, tile_set: TileSet, tile_size: int, ctx: Co
     used = set()
     while heap:
         d, n, q = heapq.heappop(heap)
-        its, ds, first = lists[q]
-        it = int(its[ptr[q] - first])
+        its, ds = lists[q]
+        it = int(its[ptr[q]])
         if abs(it) not in used:
             used.add(abs(it))
+            retired[abs(it) - 1] = 1
             item[q], dist[q] = it, d
             continue
         ptr[q] += 1
-        if ptr[q] >= L:
-            continue                                             # out of candidates: the block stays black
-        if ptr[q] - first >= len(its):                           # next page of this block's list (compute_nearest refill, :384-386)
+        if ptr[q] >= len(its):
+            # page used up: the k nearest candidates among the tiles still free — the reference's refill on the pruned
+            # tree (compute_nearest(n, 10), :384-386).  Everything this block skipped so far was taken, so the list of
+            # free candidates continues exactly where the block stands.  (Refilling other half-consumed blocks in the
+            # same launch was tried and is 10x slower: the pages are re-fetched far more often than they run dry.)
+            if len(used) >= T:
+                continue                                         # out of tiles: the block stays black
             by, bx = divmod(q, bw)
             blk = np.ascontiguousarray(source_img[by * dim:(by + 1) * dim, bx * dim:(bx + 1) * dim])
-            k = max(1, min(2 * len(its), L - ptr[q], 1024))
-            pi, pd = ctx.topk(blk, ptr[q], k)
-            its, ds, first = pi[0], pd[0], ptr[q]
-            lists[q] = (its, ds, first)
-        heapq.heappush(heap, (int(ds[ptr[q] - first]), n, q))
+            pi, pd = ctx.topk(blk, 0, max(1, min(2 * len(its), 1024)), exclude=retired)
+            its, ds = pi[0], pd[0]
+            lists[q] = (its, ds)
+            ptr[q] = 0
+        if int(its[ptr[q]]) == 0:
+            continue                                             # end of the list: nothing left for this block
+        heapq.heappush(heap, (int(ds[ptr[q]]), n, q))
     item = item.reshape(bh, bw)
     dist = dist.reshape(bh, bw)
     placed = item != 0

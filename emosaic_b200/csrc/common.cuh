@@ -102,8 +102,8 @@ int emo_launch_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t 
 int emo_launch_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4);
 int emo_launch_build_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px);
 int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);
-int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, int32_t *item,
-                    uint32_t *dist);
+int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, const uint8_t *exclude,
+                    int32_t *item, uint32_t *dist);
 int emo_launch_build_index(emo_ctx *ctx);
 int emo_prepare_match(emo_ctx *ctx, uint64_t queries);  // builds the 1to1 index when the mode / size rule asks for it
 bool emo_index_supported(const emo_ctx *ctx);

@@ -446,15 +446,17 @@ static int check_topk_args(emo_ctx *ctx, const void *src, uint32_t W, uint32_t H
     return EMO_OK;
 }
 
-int emo_topk_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, int32_t *item, uint32_t *dist) {
+int emo_topk_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, const uint8_t *exclude,
+                 int32_t *item, uint32_t *dist) {
     int rc = check_topk_args(ctx, src, W, H, k, item, dist);
     if (rc) return rc;
     EMO_REQUIRE((uintptr_t)item % 4 == 0 && (uintptr_t)dist % 4 == 0, EMO_ERR_ARG, "topk: item/dist must be 4-byte aligned");
     EMO_CK(cudaSetDevice(ctx->device));
-    return emo_launch_topk(ctx, src, W, H, first, k, item, dist);
+    return emo_launch_topk(ctx, src, W, H, first, k, exclude, item, dist);
 }
 
-int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, int32_t *item, uint32_t *dist) {
+int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, const uint8_t *exclude, int32_t *item,
+             uint32_t *dist) {
     int rc = check_topk_args(ctx, src, W, H, k, item, dist);
     if (rc) return rc;
     EMO_CK(cudaSetDevice(ctx->device));
@@ -463,7 +465,14 @@ int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t 
     if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], ob))) return rc;
     if ((rc = emo_ensure(ctx, &ctx->stage[4], &ctx->stage_cap[4], ob))) return rc;
     EMO_CK(cudaMemcpyAsync(ctx->stage[2], src, sb, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = emo_launch_topk(ctx, (const uint8_t *)ctx->stage[2], W, H, first, k, (int32_t *)ctx->stage[3], (uint32_t *)ctx->stage[4])))
+    const uint8_t *dex = nullptr;
+    if (exclude) {
+        if ((rc = emo_ensure(ctx, &ctx->stage[5], &ctx->stage_cap[5], ctx->T))) return rc;
+        EMO_CK(cudaMemcpyAsync(ctx->stage[5], exclude, ctx->T, cudaMemcpyHostToDevice, ctx->stream));
+        dex = (const uint8_t *)ctx->stage[5];
+    }
+    if ((rc = emo_launch_topk(ctx, (const uint8_t *)ctx->stage[2], W, H, first, k, dex, (int32_t *)ctx->stage[3],
+                              (uint32_t *)ctx->stage[4])))
         return rc;
     EMO_CK(cudaMemcpyAsync(item, ctx->stage[3], ob, cudaMemcpyDeviceToHost, ctx->stream));
     EMO_CK(cudaMemcpyAsync(dist, ctx->stage[4], ob, cudaMemcpyDeviceToHost, ctx->stream));

@@ -7,8 +7,10 @@
 // entries of a list, so this kernel serves the lists in pages: for every block the candidates at positions
 // [first, first + k) of its list ordered by (distance, insertion rank).  Insertion rank = 2t for tile t, 2t + 1 for its
 // mirror (tileset.rs:178-190); kiddo's own order among equal distances is unpinned and this is the
-// canonical one the oracle uses.  For N == 1 a tile and its mirror have the same vector: the mirror sits directly
-// behind the tile in every list and using one retires both (rendering.rs:357-358), so it is omitted.
+// canonical one the oracle uses.  `exclude` ([T] bytes, optional) removes the candidates of retired tiles from every
+// list — the reference removes a placed tile from the tree (:366-380), so its refill sees the pruned set.  For N == 1
+// a tile and its mirror have the same vector: the mirror sits directly behind the tile in every list and using one
+// retires both (rendering.rs:357-358), so it is omitted.
 //
 // One CTA per block.  The block's query vector stays in registers; candidates are read from the packed array built
 // by emo_set_library (L2-resident).  Keys are (distance << 31 | rank), unique per candidate, so the k-th key is found
@@ -29,9 +31,16 @@ struct TopkParams {
     const uint8_t *src;    // [H][W][3]
     uint32_t W, dim, bw, N;
     uint32_t first, k;
+    const uint8_t *exclude;  // [T] or nullptr: 1 = tile retired (both orientations), its candidates do not exist
     int32_t *item;   // [Q][k]
     uint32_t *dist;  // [Q][k]
 };
+
+template <bool EXCL>
+__device__ __forceinline__ bool topk_alive(const TopkParams &p, uint32_t c) {
+    if (!EXCL) return true;
+    return __ldg(p.exclude + (p.mirrored ? (c >> 1) : c)) == 0;
+}
 
 template <int WORDS>
 __device__ __forceinline__ unsigned long long topk_key(const uint32_t (&q)[WORDS], const uint32_t *__restrict__ cand, uint32_t c) {
@@ -42,7 +51,7 @@ __device__ __forceinline__ unsigned long long topk_key(const uint32_t (&q)[WORDS
 }
 
 // the key at sorted position `pos` (0-based) among the L keys; every thread returns it
-template <int WORDS>
+template <int WORDS, bool EXCL>
 __device__ unsigned long long topk_select(const uint32_t (&q)[WORDS], const TopkParams &p, uint32_t pos, uint32_t *hist, uint32_t *scratch) {
     unsigned long long prefix = 0, mask = 0;
     uint32_t remaining = pos;
@@ -52,6 +61,7 @@ __device__ unsigned long long topk_select(const uint32_t (&q)[WORDS], const Topk
         for (int b = tid; b < TOPK_BINS; b += TOPK_THREADS) hist[b] = 0;
         __syncthreads();
         for (uint32_t c = tid; c < p.L; c += TOPK_THREADS) {
+            if (!topk_alive<EXCL>(p, c)) continue;
             const unsigned long long key = topk_key<WORDS>(q, p.cand, c);
             if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & (TOPK_BINS - 1)], 1u);
         }
@@ -92,7 +102,7 @@ __device__ unsigned long long topk_select(const uint32_t (&q)[WORDS], const Topk
     return prefix;
 }
 
-template <int WORDS>
+template <int WORDS, bool EXCL>
 __global__ void __launch_bounds__(TOPK_THREADS) topk_kernel(const TopkParams p) {
     __shared__ uint32_t hist[TOPK_BINS];
     __shared__ unsigned long long keys[TOPK_MAX_K];
@@ -119,17 +129,29 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_kernel(const TopkParams p) 
 
     int32_t *item = p.item + (size_t)blk * p.k;
     uint32_t *dist = p.dist + (size_t)blk * p.k;
+    // candidates that exist for this call (all of them, or those of the tiles not retired yet)
+    uint32_t alive = p.L;
+    if (EXCL) {
+        if (tid == 0) scratch[11] = 0;
+        __syncthreads();
+        uint32_t mine = 0;
+        for (uint32_t c = tid; c < p.L; c += TOPK_THREADS) mine += topk_alive<EXCL>(p, c) ? 1u : 0u;
+        atomicAdd(&scratch[11], mine);
+        __syncthreads();
+        alive = scratch[11];
+    }
     uint32_t n = 0;  // entries of this page that exist
-    if (p.first < p.L) n = min(p.k, p.L - p.first);
+    if (p.first < alive) n = min(p.k, alive - p.first);
     if (n > 0) {
-        const unsigned long long lo = topk_select<WORDS>(q, p, p.first, hist, scratch);
-        const unsigned long long hi = n > 1 ? topk_select<WORDS>(q, p, p.first + n - 1, hist, scratch) : lo;
+        const unsigned long long lo = topk_select<WORDS, EXCL>(q, p, p.first, hist, scratch);
+        const unsigned long long hi = n > 1 ? topk_select<WORDS, EXCL>(q, p, p.first + n - 1, hist, scratch) : lo;
         if (tid == 0) scratch[10] = 0;
         uint32_t m = 1;
         while (m < n) m <<= 1;
         for (uint32_t j = tid; j < m; j += TOPK_THREADS) keys[j] = ~0ull;
         __syncthreads();
         for (uint32_t c = tid; c < p.L; c += TOPK_THREADS) {
+            if (!topk_alive<EXCL>(p, c)) continue;
             const unsigned long long key = topk_key<WORDS>(q, p.cand, c);
             if (key >= lo && key <= hi) keys[atomicAdd(&scratch[10], 1u)] = key;  // exactly n keys qualify
         }
@@ -165,8 +187,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_kernel(const TopkParams p) 
     }
 }
 
-int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, int32_t *item,
-                    uint32_t *dist) {
+int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, const uint8_t *exclude,
+                    int32_t *item, uint32_t *dist) {
     TopkParams p;
     p.cand = ctx->cand;
     p.L = ctx->L;
@@ -178,14 +200,16 @@ int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, ui
     p.N = ctx->N;
     p.first = first;
     p.k = k;
+    p.exclude = exclude;
     p.item = item;
     p.dist = dist;
     const uint32_t Q = p.bw * (H / ctx->dim);
+    const bool ex = exclude != nullptr;
     switch (ctx->words) {
-        case 1: topk_kernel<1><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
-        case 3: topk_kernel<3><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
-        case 7: topk_kernel<7><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
-        case 12: topk_kernel<12><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
+        case 1: ex ? topk_kernel<1, true><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p) : topk_kernel<1, false><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
+        case 3: ex ? topk_kernel<3, true><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p) : topk_kernel<3, false><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
+        case 7: ex ? topk_kernel<7, true><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p) : topk_kernel<7, false><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
+        case 12: ex ? topk_kernel<12, true><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p) : topk_kernel<12, false><<<Q, TOPK_THREADS, 0, ctx->stream>>>(p); break;
         default:
             emo_set_error("topk: ranked lists exist for --mode 1..4 (N = 1, 4, 9, 16), not N=%u", ctx->N);
             return EMO_ERR_UNSUPPORTED;

@@ -139,14 +139,17 @@ int emo_match_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, 
  * its mirror (tileset.rs:178-190; the order among equal distances is this library's canonical
  * one).  item_out/dist_out are [H/dim * W/dim][k], blocks row-major (by * bw + bx);
  * positions past the end of the list hold item 0 / dist 0xFFFFFFFF.  1 <= k <= 1024.
+ * exclude (NULL or [T] bytes): 1 = tile retired; its candidates (both orientations) are left out of
+ * every list, as the reference removes a placed tile from the tree (rendering.rs:366-380) before the
+ * next refill.
  * N = 1, 4, 9, 16 (--mode 1..4); EMO_ERR_UNSUPPORTED otherwise.  For N == 1 the mirrored twin of a
  * tile (same vector, directly behind it in every list) is omitted: using a tile retires both
  * orientations (rendering.rs:357-358).  The greedy assignment that consumes the lists
  * (rendering.rs:341-392) is sequential and lives in the host layers (render_nto1_no_repeat). */
 int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k,
-             int32_t *item_out, uint32_t *dist_out);
+             const uint8_t *exclude, int32_t *item_out, uint32_t *dist_out);
 int emo_topk_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, uint32_t first, uint32_t k,
-                 int32_t *item_out_dev, uint32_t *dist_out_dev);
+                 const uint8_t *exclude_dev, int32_t *item_out_dev, uint32_t *dist_out_dev);
 
 /* ---- (4) compose (+tint) -----------------------------------------------------------------
  * Replaces render() (src/mosaic/rendering.rs:51-101) + TileSet::get_image()

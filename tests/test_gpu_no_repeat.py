@@ -60,6 +60,31 @@ def test_topk_heavy_ties(ctx):
     assert (gi[0] == want).all() and (gd[0] == 9 * 12).all()
 
 
+@pytest.mark.parametrize("N,T", [(1, 500), (4, 300), (9, 64)])
+def test_topk_excluding_retired_tiles(ctx, N, T):
+    """exclude = the tiles already placed: their candidates (both orientations) vanish from every list, which is what the
+    reference's refill sees after tree.remove (rendering.rs:366-386)."""
+    dim = int(N ** 0.5)
+    rng = np.random.default_rng(N + T)
+    colors = rng.integers(0, 256, (T, N, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (3 * dim, 4 * dim, 3), dtype=np.uint8)
+    ctx.set_library(colors)
+    ei, ed = expected_lists(colors, src)
+    for frac in (0.0, 0.3, 0.9, 1.0):
+        retired = (rng.random(T) < frac).astype(np.uint8)
+        if frac == 1.0:
+            retired[:] = 1
+        for first, k in [(0, 50), (7, 200)]:
+            gi, gd = ctx.topk(src, first, k, exclude=retired)
+            for q in range(ei.shape[0]):
+                keep = retired[np.abs(ei[q]) - 1] == 0
+                wi, wd = ei[q][keep][first:first + k], ed[q][keep][first:first + k]
+                assert (gi[q, :wi.size] == wi).all() and (gd[q, :wi.size] == wd).all(), (frac, first, k, q)
+                assert (gi[q, wi.size:] == 0).all() and (gd[q, wi.size:] == 0xFFFFFFFF).all()
+    with pytest.raises(emo.EmosaicError, match="one byte per tile"):
+        ctx.topk(src, 0, 4, exclude=np.zeros(T + 1, np.uint8))
+
+
 def test_topk_first_entry_is_the_match(ctx):
     rng = np.random.default_rng(8)
     colors = rng.integers(0, 256, (5000, 4, 3), dtype=np.uint8)
