@@ -573,6 +573,27 @@ def extras(ctx, torch, dev, hbm_peak, peak_src):
                          "int_ops_per_s": 2 * 12 * Q2 * 2 * T2 / (m_ms * 1e-3)}
     except Exception as e:  # noqa: BLE001
         ex["c2_4to1"] = {"error": str(e)}
+
+    # Lanczos3 resize (image 0.25.2 imageops::resize, bit-exact): the source step of main.rs:567-595 on a C4-sized image that is
+    # not divisible (4098 x 4097 -> 4096 x 4096) and tile preparation (tiles/utils.rs:188-189) of 64 photos of 2048^2 -> 64^2.
+    # Bound: the exactness contract forbids FMA and fixes the tap order, so the vertical pass costs 2 FP32 instructions per tap
+    # (6 taps per source byte when shrinking) — an FP32-pipe bound, reported as algorithmic bytes/s next to the HBM peak.
+    try:
+        rs = {}
+        for name, n, h, w, nh, nw in (("source_4098x4097_to_4096", 1, 4097, 4098, 4096, 4096), ("tiles_64x2048sq_to_64", 64, 2048, 2048, 64, 64)):
+            g = torch.Generator(device=dev); g.manual_seed(77)
+            imgs = torch.randint(0, 256, (n * h * w * 3,), dtype=torch.uint8, device=dev, generator=g)
+            outr = torch.empty(n * nh * nw * 3, dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            ms = timeit(lambda: ctx.resize_dev(imgs.data_ptr(), n, w, h, None, nw, nh, outr.data_ptr()))
+            byt = n * (h * w * 3 + nh * nw * 3)
+            rs[name] = {"ms": ms, "algorithmic_gbs": byt / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byt / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "source_mpx_per_s": n * h * w / (ms * 1e-3) / 1e6}
+            del imgs, outr
+            torch.cuda.empty_cache()
+        ex["resize_lanczos3"] = rs
+    except Exception as e:  # noqa: BLE001
+        ex["resize_lanczos3"] = {"error": str(e)}
     return ex
 
 

@@ -133,6 +133,26 @@ class Context:
         check(self._lib.emo_probe_int_pipe(self._h, which, C.byref(v)))
         return float(v.value)
 
+    # -- (0) Lanczos3 resize --------------------------------------------------------------
+    def resize(self, images, nw: int, nh: int, view=None) -> np.ndarray:
+        """image 0.25.2 ``imageops::resize(view, nw, nh, Lanczos3)`` (main.rs:595, tiles/utils.rs:188-189).
+        images [H,W,3] or a batch [n,H,W,3]; view = (x0, y0, cw, ch) applied to every image, default the whole image."""
+        images = _u8(images)
+        single = images.ndim == 3
+        if single:
+            images = images[None]
+        if images.ndim != 4 or images.shape[3] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"images must be [H,W,3] or [n,H,W,3], got {images.shape}")
+        n, H, W = images.shape[:3]
+        x0, y0, cw, ch = view if view is not None else (0, 0, W, H)
+        out = np.zeros((n, nh, nw, 3), np.uint8)
+        check(self._lib.emo_resize(self._h, _ptr(images), n, W, H, x0, y0, cw, ch, nw, nh, _ptr(out)))
+        return out[0] if single else out
+
+    def resize_dev(self, images_dev: int, n: int, W: int, H: int, view, nw: int, nh: int, out_dev: int):
+        x0, y0, cw, ch = view if view is not None else (0, 0, W, H)
+        check(self._lib.emo_resize_dev(self._h, C.c_void_p(images_dev), n, W, H, x0, y0, cw, ch, nw, nh, C.c_void_p(out_dev)))
+
     # -- (1) analysis ---------------------------------------------------------------------
     def analyse_tiles(self, tiles, dim: int) -> np.ndarray:
         """tiles [T,ts,ts,3] -> [T,dim*dim,3]  (analysis.rs:5-20 over the library, main.rs:786-794)."""
@@ -429,6 +449,73 @@ def adjust_source_dims(w: int, h: int, downsample: int, dim: int):
     m = nh % dim
     nh = nh + dim - m if m > dim // 2 else nh - m
     return nw, nh
+
+
+def resize_source(original_img, downsample: int, dim: int, ctx: Context | None = None) -> np.ndarray:
+    """main.rs:567-595: the copy of the source that is matched — ``imageops::resize(original, nw, nh, Lanczos3)`` with
+    (nw, nh) from the dimension rule; equal dimensions give a plain copy, as in the crate."""
+    original_img = _u8(original_img)
+    nw, nh = adjust_source_dims(original_img.shape[1], original_img.shape[0], downsample, dim)
+    if nw == 0 or nh == 0:
+        raise EmosaicError(EMO_ERR_ARG, f"Invalid source dimensions ({original_img.shape[1]}x{original_img.shape[0]}): nothing "
+                           f"left after downsampling by {downsample} to a multiple of {dim}")
+    return (ctx or default_context()).resize(original_img, nw, nh)
+
+
+def _most_common_value(values: np.ndarray) -> int:
+    """tiles/utils.rs:262-273.  HashMap + max_by_key leaves the winner among equally frequent values to the hash order;
+    the canonical rule is the smallest such value.  Empty input -> 0 (``unwrap_or((0, 0)).0``)."""
+    if values.size == 0:
+        return 0
+    vals, counts = np.unique(values, return_counts=True)
+    return int(vals[np.argmax(counts)])
+
+
+def prepare_view(img, tile_size: int, crop: bool):
+    """The view of a decoded photo that ``prepare_tile`` resizes (tiles/utils.rs:93-186): white borders (every channel
+    > 240) are trimmed to the most common first / last non-white column and row — the view is [first, last) on both
+    axes — then ``crop`` takes the centred largest square.  Host-side index bookkeeping; no pixel is produced here."""
+    img = _u8(img)
+    h, w = img.shape[:2]
+    if w < tile_size or h < tile_size:  # utils.rs:99-106
+        raise EmosaicError(EMO_ERR_ARG, f"Image {w}x{h} is smaller than the tile size {tile_size} (DimensionError)")
+    nonwhite = ~((img[..., 0] > 240) & (img[..., 1] > 240) & (img[..., 2] > 240))
+
+    def first_last(m):
+        n = m.shape[1]
+        has = m.any(axis=1)
+        return np.where(has, m.argmax(axis=1), n), np.where(has, n - 1 - m[:, ::-1].argmax(axis=1), 0)
+
+    from_left, from_right = first_last(nonwhite)
+    from_top, from_bottom = first_last(nonwhite.T)
+    c0 = _most_common_value(from_left[from_left != w])
+    c1 = _most_common_value(from_right[from_right != 0])
+    r0 = _most_common_value(from_top[from_top != h])
+    r1 = _most_common_value(from_bottom[from_bottom != 0])
+    if not (c0 < c1 and r0 < r1):  # utils.rs:157-158 assert!
+        raise EmosaicError(EMO_ERR_ARG, "assertion failed: first_non_white_col < last_non_white_col / first_non_white_row < "
+                           "last_non_white_row (no non-white interior)")
+    vx, vy, vw, vh = c0, r0, c1 - c0, r1 - r0
+    if crop:  # utils.rs:170-182
+        size = min(vw, vh)
+        vx, vy, vw, vh = vx + (vw - size) // 2, vy + (vh - size) // 2, size, size
+    return vx, vy, vw, vh
+
+
+def rotate(img: np.ndarray, orientation: int) -> np.ndarray:
+    """tiles/utils.rs:248-264: undo the EXIF orientation (1..8) of an already resized tile."""
+    r90 = lambda a: np.rot90(a, -1)   # imageops::rotate90 = clockwise
+    r270 = lambda a: np.rot90(a, 1)
+    ops = {2: lambda a: a[:, ::-1], 3: lambda a: a[::-1, ::-1], 4: lambda a: a[::-1],
+           5: lambda a: r90(a)[:, ::-1], 6: r90, 7: lambda a: r270(a)[:, ::-1], 8: r270}
+    return np.ascontiguousarray(ops.get(orientation, lambda a: a)(img))
+
+
+def prepare_tile(img, tile_size: int, crop: bool, orientation: int = 1, ctx: Context | None = None) -> np.ndarray:
+    """``prepare_tile`` (tiles/utils.rs:63-196) from the decoded photo on: trim + crop view, Lanczos3 resize to
+    tile_size x tile_size on the GPU, EXIF rotation.  File read, MD5 and the JPEG cache stay in the caller."""
+    view = prepare_view(img, tile_size, crop)
+    return rotate((ctx or default_context()).resize(img, tile_size, tile_size, view), orientation)
 
 
 def tint_alpha(tint_opacity: float) -> int:

@@ -5,9 +5,10 @@
     python -m emosaic_b200 ... IMG mosaic TILES_DIR -m 1to1|4to1|random        (README spelling)
 
 Mirrors src/main.rs:28-138 (flags), :542-667 (n_to_1: dimension rule, cache, render) and :447-478 (tint).
-Decoding, resizing and directory walking stay on the host (PIL) and outside the accelerated path; tile
-preparation here is decode -> EXIF transpose -> optional centre-square crop -> Lanczos resize (the reference's
-white-border trimming and its ~/.cache/mosaic JPEG cache are host stages that are not reproduced).
+Decoding (PIL) and directory walking stay on the host and outside the accelerated path.  Both Lanczos3 resizes of the
+reference run on the GPU (emo_resize, bit-exact with image 0.25.2): the source image (main.rs:595) and tile preparation
+(tiles/utils.rs:63-196: white-border trim view, optional centre-square crop, resize, EXIF rotation); the reference's
+~/.cache/mosaic JPEG cache of prepared tiles is not reproduced (every run prepares from the original file).
 --no-repeat runs the no-repeat renderer (rendering.rs:262-401); --randomize / --greedy / --html / --web are rejected:
 outside the accelerated path.
 """
@@ -39,14 +40,17 @@ def find_images(root: str, extensions) -> List[str]:
     return out
 
 
-def prepare_tile(path: str, tile_size: int, crop: bool) -> np.ndarray:
-    from PIL import Image, ImageOps
-    im = ImageOps.exif_transpose(Image.open(path)).convert("RGB")
-    if crop:
-        w, h = im.size
-        s = min(w, h)
-        im = im.crop(((w - s) // 2, (h - s) // 2, (w - s) // 2 + s, (h - s) // 2 + s))
-    return np.asarray(im.resize((tile_size, tile_size), Image.LANCZOS), dtype=np.uint8)
+def prepare_tile(path: str, tile_size: int, crop: bool, ctx: Optional[api.Context] = None) -> np.ndarray:
+    """tiles/utils.rs:63-196 without the JPEG cache: decode (host), then trim view / crop / Lanczos3 resize (GPU) / rotate."""
+    from PIL import Image
+    im = Image.open(path)
+    try:
+        orientation = int(im.getexif().get(274, 1))  # utils.rs:198-212 get_jpeg_orientation: 1..8, else 1
+    except Exception:
+        orientation = 1
+    if not 1 <= orientation <= 8:
+        orientation = 1
+    return api.prepare_tile(np.asarray(im.convert("RGB"), dtype=np.uint8), tile_size, crop, orientation, ctx)
 
 
 def exif_date(path: str) -> Optional[str]:
@@ -107,7 +111,11 @@ def main(argv=None) -> int:
         print(f"error: Output directory does not exist: {out_parent}", file=sys.stderr)
         return 1
     if args.subcmd == "prepare":
-        Image.fromarray(prepare_tile(args.img, ts, args.crop)).save(args.output_path)
+        try:
+            Image.fromarray(prepare_tile(args.img, ts, args.crop, api.Context(args.device))).save(args.output_path)
+        except api.EmosaicError as e:
+            print(f"error: {e}", file=sys.stderr)
+            return 1
         return 0
     if args.subcmd != "mosaic":
         print("error: a subcommand is required (mosaic | prepare)", file=sys.stderr)
@@ -132,7 +140,7 @@ def main(argv=None) -> int:
     if mode == "random":  # main.rs:414-442 + rendering.rs:418-440: uniform random tile per source pixel
         paths = [p for p in find_images(args.tiles_dir, exts) if os.path.exists(p)]
         print(f"Tile set with {len(paths)} tiles", file=sys.stderr)
-        px = np.stack([prepare_tile(p, ts, True) for p in paths])
+        px = np.stack([prepare_tile(p, ts, True, ctx) for p in paths])
         ctx.set_library(np.zeros((len(paths), 1, 3), np.uint8), px)
         item = np.random.default_rng(args.seed).integers(1, len(paths) + 1, original.shape[:2]).astype(np.int32)
         out = ctx.compose(item)
@@ -142,8 +150,11 @@ def main(argv=None) -> int:
         N = dim * dim
         nw, nh = api.adjust_source_dims(original.shape[1], original.shape[0], args.downsample, dim)  # main.rs:567-587
         print(f"Resizing source image from {original.shape[1]}x{original.shape[0]} to {nw}x{nh}", file=sys.stderr)
-        img = original if (nw, nh) == (original.shape[1], original.shape[0]) else np.asarray(
-            Image.fromarray(original).resize((nw, nh), Image.LANCZOS), dtype=np.uint8)
+        try:
+            img = api.resize_source(original, args.downsample, dim, ctx)  # main.rs:595 imageops::resize(Lanczos3), on the GPU
+        except api.EmosaicError as e:
+            print(f"error: {e}", file=sys.stderr)
+            return 1
         if img.shape[1] % dim or img.shape[0] % dim:
             print(f"Invalid source dimensions ({img.shape[1]}x{img.shape[0]}): Dimensions must be divisible by {dim}", file=sys.stderr)
             return 1
@@ -160,7 +171,7 @@ def main(argv=None) -> int:
                 colors = None
         if colors is None:  # generate_tile_set, main.rs:740-813, analysis on the GPU in one batch
             paths = find_images(args.tiles_dir, exts)
-            px = np.stack([prepare_tile(p, ts, args.crop) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
+            px = np.stack([prepare_tile(p, ts, args.crop, ctx) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
             dates = [exif_date(p) for p in paths]
             colors = ctx.analyse_tiles(px, dim)
             with open(cache_path, "wb") as f:
@@ -170,7 +181,7 @@ def main(argv=None) -> int:
         # tileset.rs:152-155: a TileSet built by from_tiles holds no images, so rendering always (re)prepares
         # the tiles with crop = true, whatever --crop was used for the analysis
         if px_render is None:
-            px_render = np.stack([prepare_tile(p, ts, True) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
+            px_render = np.stack([prepare_tile(p, ts, True, ctx) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
         px = px_render
         print(f"Tile set with {len(paths)} tiles", file=sys.stderr)
         if len(paths) == 0:

@@ -54,6 +54,8 @@ struct emo_tint_tables {
     uint32_t *meta = nullptr; // [0] = max exceptions per fg, [1] = alpha byte, [2] = sanity errors, [3] = non-uniform fg (device)
 };
 
+struct emo_resize_state;  // resize.cu: cached tap tables + the f32 intermediate image
+
 struct emo_ctx {
     int device = 0;
     int sm_count = 0;
@@ -92,6 +94,7 @@ struct emo_ctx {
     size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
 
     emo_tint_tables tint;
+    emo_resize_state *resize = nullptr;
 };
 
 int emo_ensure(emo_ctx *ctx, void **p, size_t *cap, size_t bytes);  // grow-only device buffer
@@ -100,6 +103,9 @@ int emo_check_device_flag(emo_ctx *ctx);
 // kernels' host launchers (device pointers, async on ctx->stream)
 int emo_launch_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out);
 int emo_launch_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4);
+int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0, uint32_t y0,
+                      uint32_t cw, uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out);
+void emo_resize_state_free(emo_resize_state *s);
 int emo_launch_build_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px);
 int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);
 int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, const uint8_t *exclude,

@@ -72,6 +72,7 @@ void emo_destroy(emo_ctx *ctx) {
     cudaFree(ctx->tint.excm);
     cudaFree(ctx->tint.cadd);
     cudaFree(ctx->tint.meta);
+    emo_resize_state_free(ctx->resize);
     for (int i = 0; i < 4; i++)
         if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
     for (cudaEvent_t e : ctx->marks)
@@ -302,6 +303,64 @@ int emo_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t t
     if (T == 0) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
     return analyse_host(ctx, tiles, T, ts, 2, out1, out4, true);
+}
+
+// ---- Lanczos3 resize (image 0.25.2 imageops::resize; main.rs:595, tiles/utils.rs:188-189) -----------------------------
+static int check_resize_args(emo_ctx *ctx, const void *images, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0, uint32_t y0,
+                             uint32_t cw, uint32_t ch, uint32_t nw, uint32_t nh, const void *out) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "resize: ctx is NULL");
+    EMO_REQUIRE(n == 0 || (images && out), EMO_ERR_ARG, "resize: NULL buffer");
+    EMO_REQUIRE(img_w >= 1 && img_h >= 1 && cw >= 1 && ch >= 1 && nw >= 1 && nh >= 1, EMO_ERR_ARG,
+                "resize: empty image, view or output (%ux%u, view %ux%u -> %ux%u)", img_w, img_h, cw, ch, nw, nh);
+    EMO_REQUIRE((uint64_t)x0 + cw <= img_w && (uint64_t)y0 + ch <= img_h, EMO_ERR_ARG,
+                "resize: view (%u,%u,%u,%u) extends beyond the %ux%u image", x0, y0, cw, ch, img_w, img_h);
+    if (img_w > (1u << 24) || img_h > 65535 || nh > 65535 || nw > (1u << 24)) {
+        emo_set_error("resize: dimensions beyond 2^24 columns / 65535 rows are not supported (%ux%u -> %ux%u)", img_w, img_h, nw, nh);
+        return EMO_ERR_UNSUPPORTED;
+    }
+    return EMO_OK;
+}
+
+int emo_resize_dev(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0, uint32_t y0,
+                   uint32_t cw, uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out) {
+    int rc = check_resize_args(ctx, images, n, img_w, img_h, x0, y0, cw, ch, nw, nh, out);
+    if (rc) return rc;
+    if (n == 0) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    return emo_launch_resize(ctx, images, n, img_w, img_h, x0, y0, cw, ch, nw, nh, out);
+}
+
+// Host pointers: images go up in slabs of ~256 MB on the copy stream while the previous slab is resized (the same two-slab
+// pipeline as analyse_host), results come back per slab.
+int emo_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0, uint32_t y0, uint32_t cw,
+               uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out) {
+    int rc = check_resize_args(ctx, images, n, img_w, img_h, x0, y0, cw, ch, nw, nh, out);
+    if (rc) return rc;
+    if (n == 0) return EMO_OK;
+    EMO_CK(cudaSetDevice(ctx->device));
+    const size_t img_b = (size_t)img_w * img_h * 3, out_b = (size_t)nw * nh * 3;
+    uint32_t slab = (uint32_t)((256ull << 20) / img_b);
+    if (slab < 1) slab = 1;
+    if (slab > n) slab = n;
+    if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], 2 * slab * img_b))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], 2 * slab * out_b))) return rc;
+    uint8_t *din[2] = {(uint8_t *)ctx->stage[0], (uint8_t *)ctx->stage[0] + slab * img_b};
+    uint8_t *dout[2] = {(uint8_t *)ctx->stage[1], (uint8_t *)ctx->stage[1] + slab * out_b};
+    uint32_t k = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += slab, k++) {
+        const uint32_t m = n - i0 < slab ? n - i0 : slab;
+        const int b = k & 1;
+        if (k >= 2) EMO_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[2 + b], 0));
+        EMO_CK(cudaMemcpyAsync(din[b], images + (size_t)i0 * img_b, m * img_b, cudaMemcpyHostToDevice, ctx->copy_stream));
+        EMO_CK(cudaEventRecord(ctx->ev_pipe[b], ctx->copy_stream));
+        EMO_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[b], 0));
+        if ((rc = emo_launch_resize(ctx, din[b], m, img_w, img_h, x0, y0, cw, ch, nw, nh, dout[b]))) return rc;
+        EMO_CK(cudaMemcpyAsync(out + (size_t)i0 * out_b, dout[b], m * out_b, cudaMemcpyDeviceToHost, ctx->stream));
+        EMO_CK(cudaEventRecord(ctx->ev_pipe[2 + b], ctx->stream));
+    }
+    EMO_CK(cudaStreamSynchronize(ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->copy_stream));
+    return EMO_OK;
 }
 
 static int check_library_args(const void *colors, uint32_t T, uint32_t N, uint32_t ts, const void *px) {

@@ -1,8 +1,11 @@
 // cli.cpp — `emosaic` with the reference's command line (src/main.rs:28-138) for the accelerated path, C++ host.
-//   emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m 1|2|...|128|1to1|4to1|random] [-f] [-t X] [--extensions e ...]
-// Tiles and the source are decoded by the minimal PNG/PPM reader of emosaic.cpp and must already be tile_size x
-// tile_size (decode/trim/crop/Lanczos3 = prepare_tile is a host stage outside the accelerated path; the Python front
-// end `python -m emosaic_b200` does it with PIL, including JPEG).  Cache files are byte-compatible.
+//   emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m 1|2|...|128|1to1|4to1|random] [-f] [-t X] [--downsample K]
+//           [--extensions e ...]
+// Tiles and the source are decoded by the minimal PNG/PPM reader of emosaic.cpp (no libjpeg in this image; the Python
+// front end `python -m emosaic_b200` decodes JPEG with PIL).  A tile that is already tile_size x tile_size is taken as
+// prepared (the role of the reference's ~/.cache/mosaic hit, utils.rs:73-85); any other tile goes through prepare_tile
+// (trim view, crop, Lanczos3 resize on the GPU).  The source is resized like main.rs:567-595.  Cache files are
+// byte-compatible.
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -41,6 +44,7 @@ int main(int argc, char **argv) {
     std::string output = "./output.jpg", img_path, tiles_dir, mode = "1";
     bool crop = false, force = false, mosaic = false, no_repeat = false;
     double tint = 0.0;
+    uint32_t downsample = 1;
     std::vector<std::string> exts = {"jpg", "jpeg"}, pos;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -52,6 +56,7 @@ int main(int argc, char **argv) {
         else if (a == "-f" || a == "--force") force = true;
         else if (a == "-t" || a == "--tint-opacity") tint = std::stod(next());
         else if (a == "--extensions") { exts.clear(); while (i + 1 < argc && argv[i + 1][0] != '-') exts.push_back(argv[++i]); }
+        else if (a == "--downsample") downsample = (uint32_t)std::stoul(next());
         else if (a == "--no-repeat") no_repeat = true;  // main.rs:663-664: render_nto1_no_repeat
         else if (a == "--randomize" || a == "--greedy" || a == "--html" || a == "--web") {
             fprintf(stderr, "error: %s is outside the accelerated path\n", a.c_str());
@@ -64,28 +69,29 @@ int main(int argc, char **argv) {
         return 2;
     }
     if (!(tint >= 0.0 && tint <= 1.0)) { fprintf(stderr, "error: Value must be between 0 and 1\n"); return 2; }
+    if (downsample < 1) { fprintf(stderr, "error: --downsample must be at least 1\n"); return 2; }
     img_path = pos[0];
     tiles_dir = pos[1];
     try {
         Context ctx(0);
         const Image original = read_image(img_path);
+        // tiles/utils.rs:63-196 from the decoded image on; `crop_tile` as prepare_tile's crop argument
+        auto load_tile = [&](const std::string &p, bool crop_tile) {
+            Image t = read_image(p);
+            return (t.width == tile_size && t.height == tile_size) ? t : prepare_tile(ctx, t, tile_size, crop_tile);
+        };
         uint32_t dim = mode == "1to1" ? 1 : mode == "4to1" ? 2 : mode == "random" ? 0 : (uint32_t)std::stoul(mode);
         if (dim == 0) {  // random mode
             std::vector<std::string> paths;
             find_images(tiles_dir, exts, paths);
             TileSet ts(1);
-            for (auto &p : paths) ts.push_tile_with_image(p, {0, 0, 0}, read_image(p));
+            for (auto &p : paths) ts.push_tile_with_image(p, {0, 0, 0}, load_tile(p, true));
             fprintf(stderr, "Tile set with %zu tiles\n", ts.len());
             write_png(output, render_random(ctx, original, ts, tile_size, 0));
             return 0;
         }
         const uint32_t N = dim * dim;
-        auto [nw, nh] = adjust_dims(original.width, original.height, 1, dim);
-        if (nw != original.width || nh != original.height) {
-            fprintf(stderr, "Invalid source dimensions (%ux%u): Dimensions must be divisible by %u (resizing is a host stage)\n",
-                    original.width, original.height, dim);
-            return 1;
-        }
+        const Image source = resize_source(ctx, original, downsample, dim);  // main.rs:567-595
         const std::string cache_path = tiles_dir + "/" + cache_file_name(N, crop);
         TileSet ts(N);
         bool have = false;
@@ -96,7 +102,8 @@ int main(int argc, char **argv) {
                 try {
                     TileSet cached = deserialize_tile_set(bytes, N, &exts, true);
                     fprintf(stderr, "Reusing analysis cache\n");
-                    for (const Tile &t : cached.tiles()) ts.push_tile_with_image(cached.get_path(t), t.colors, read_image(cached.get_path(t)));
+                    // tileset.rs:152-155: a cache-loaded TileSet prepares its images with crop = true
+                    for (const Tile &t : cached.tiles()) ts.push_tile_with_image(cached.get_path(t), t.colors, load_tile(cached.get_path(t), true));
                     have = true;
                 } catch (const Error &) {
                 }
@@ -106,19 +113,23 @@ int main(int argc, char **argv) {
             std::vector<std::string> paths;
             find_images(tiles_dir, exts, paths);
             std::vector<Image> tiles;
-            for (auto &p : paths) tiles.push_back(read_image(p));
+            for (auto &p : paths) tiles.push_back(load_tile(p, crop));
             const std::vector<uint8_t> colors = analyse_tiles(ctx, tiles, N);
-            for (size_t i = 0; i < paths.size(); i++)
-                ts.push_tile_with_image(paths[i], std::vector<uint8_t>(colors.begin() + i * N * 3, colors.begin() + (i + 1) * N * 3), tiles[i]);
+            for (size_t i = 0; i < paths.size(); i++)  // rendering re-prepares with crop = true (tileset.rs:152-155)
+                ts.push_tile_with_image(paths[i], std::vector<uint8_t>(colors.begin() + i * N * 3, colors.begin() + (i + 1) * N * 3),
+                                        crop ? tiles[i] : load_tile(paths[i], true));
             const std::vector<uint8_t> blob = serialize_tile_set(ts);
             std::ofstream(cache_path, std::ios::binary).write((const char *)blob.data(), blob.size());
         }
         fprintf(stderr, "Tile set with %zu tiles\n", ts.len());
         if (no_repeat && tint > 0.0) throw Error(EMO_ERR_UNSUPPORTED, "--no-repeat with --tint-opacity is not wired in this front end");
-        RenderResult r = no_repeat ? render_nto1_no_repeat(ctx, original, ts, tile_size)
-                                   : render_nto1(ctx, original, ts, tile_size, false, std::nullopt, tint);
-        if (tint > 0.0) {  // main.rs:447-478: RGBA PNG, early return
-            write_png(output, r.image);
+        RenderResult r = no_repeat ? render_nto1_no_repeat(ctx, source, ts, tile_size)
+                                   : render_nto1(ctx, source, ts, tile_size, false, std::nullopt, 0.0);
+        if (tint > 0.0) {  // main.rs:447-478: the image as opened (not the resized copy) tints the mosaic; RGBA PNG, early return
+            Image rgba(r.image.width, r.image.height, 4);
+            check(emo_compose_overlay(ctx.handle(), r.item.data(), source.width, source.height, original.data.data(), original.width,
+                                      original.height, tint_alpha(tint), rgba.data.data()));
+            write_png(output, rgba);
             return 0;
         }
         summarise(r, ts);

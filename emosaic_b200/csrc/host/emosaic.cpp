@@ -274,6 +274,91 @@ std::pair<uint32_t, uint32_t> adjust_dims(uint32_t w, uint32_t h, uint32_t downs
     return {nw, nh};
 }
 
+// ---- resize / prepare_tile ----------------------------------------------------------------------------
+Image resize_lanczos3(Context &ctx, const Image &img, uint32_t nw, uint32_t nh, std::optional<View> view) {
+    if (img.channels != 3) throw Error(EMO_ERR_ARG, "resize: RGB images only");
+    const View v = view.value_or(View{0, 0, img.width, img.height});
+    Image out(nw, nh, 3);
+    check(emo_resize(ctx.handle(), img.data.data(), 1, img.width, img.height, v.x, v.y, v.w, v.h, nw, nh, out.data.data()));
+    return out;
+}
+
+Image resize_source(Context &ctx, const Image &original, uint32_t downsample, uint32_t dim) {
+    auto [nw, nh] = adjust_dims(original.width, original.height, downsample, dim);
+    fprintf(stderr, "Resizing source image from %ux%u to %ux%u\n", original.width, original.height, nw, nh);  // main.rs:587-593
+    return resize_lanczos3(ctx, original, nw, nh);
+}
+
+uint32_t most_common_value(const std::vector<uint32_t> &values) {
+    std::map<uint32_t, uint32_t> counts;  // ordered: the first maximum is the smallest value (canonical tie rule)
+    for (uint32_t v : values) counts[v]++;
+    uint32_t best = 0, bc = 0;            // empty input: unwrap_or((0, 0)).0
+    for (auto &[v, c] : counts)
+        if (c > bc) { bc = c; best = v; }
+    return best;
+}
+
+View prepare_view(const Image &img, uint32_t tile_size, bool crop) {
+    const uint32_t w = img.width, h = img.height;
+    if (w < tile_size || h < tile_size)  // utils.rs:99-106
+        throw Error(EMO_ERR_ARG, "Image " + std::to_string(w) + "x" + std::to_string(h) + " is smaller than the tile size (DimensionError)");
+    auto white = [&](uint32_t x, uint32_t y) { const uint8_t *p = img.pixel(x, y); return p[0] > 240 && p[1] > 240 && p[2] > 240; };
+    std::vector<uint32_t> from_left, from_right, from_top, from_bottom;
+    for (uint32_t y = 0; y < h; y++) {
+        uint32_t x = 0;
+        while (x < w && white(x, y)) x++;
+        if (x != w) from_left.push_back(x);
+        uint32_t r = 0;
+        for (uint32_t k = w; k > x; k--)
+            if (!white(k - 1, y)) { r = k - 1; break; }
+        if (r != 0) from_right.push_back(r);
+    }
+    for (uint32_t x = 0; x < w; x++) {
+        uint32_t y = 0;
+        while (y < h && white(x, y)) y++;
+        if (y != h) from_top.push_back(y);
+        uint32_t r = 0;
+        for (uint32_t k = h; k > y; k--)
+            if (!white(x, k - 1)) { r = k - 1; break; }
+        if (r != 0) from_bottom.push_back(r);
+    }
+    const uint32_t c0 = most_common_value(from_left), c1 = most_common_value(from_right), r0 = most_common_value(from_top),
+                   r1 = most_common_value(from_bottom);
+    if (!(c0 < c1)) throw Error(EMO_ERR_ARG, "assertion failed: first_non_white_col < last_non_white_col");  // utils.rs:157
+    if (!(r0 < r1)) throw Error(EMO_ERR_ARG, "assertion failed: first_non_white_row < last_non_white_row");  // utils.rs:158
+    View v{c0, r0, c1 - c0, r1 - r0};
+    if (crop) {  // utils.rs:170-182
+        const uint32_t size = std::min(v.w, v.h);
+        v = View{v.x + (v.w - size) / 2, v.y + (v.h - size) / 2, size, size};
+    }
+    return v;
+}
+
+Image rotate(const Image &img, uint32_t orientation) {
+    if (orientation < 2 || orientation > 8) return img;
+    const bool swap = orientation >= 5;
+    Image out(swap ? img.height : img.width, swap ? img.width : img.height, img.channels);
+    for (uint32_t y = 0; y < out.height; y++)
+        for (uint32_t x = 0; x < out.width; x++) {
+            uint32_t sx = x, sy = y;
+            switch (orientation) {
+                case 2: sx = img.width - 1 - x; break;                              // flip_horizontal
+                case 3: sx = img.width - 1 - x; sy = img.height - 1 - y; break;     // rotate180
+                case 4: sy = img.height - 1 - y; break;                             // flip_vertical
+                case 5: sx = y; sy = x; break;                                      // flip_horizontal(rotate90) = transpose
+                case 6: sx = y; sy = img.height - 1 - x; break;                     // rotate90 (clockwise)
+                case 7: sx = img.width - 1 - y; sy = img.height - 1 - x; break;     // flip_horizontal(rotate270) = anti-transpose
+                case 8: sx = img.width - 1 - y; sy = x; break;                      // rotate270
+            }
+            std::memcpy(out.pixel(x, y), img.pixel(sx, sy), img.channels);
+        }
+    return out;
+}
+
+Image prepare_tile(Context &ctx, const Image &decoded, uint32_t tile_size, bool crop, uint32_t orientation) {
+    return rotate(resize_lanczos3(ctx, decoded, tile_size, tile_size, prepare_view(decoded, tile_size, crop)), orientation);
+}
+
 std::string cache_file_name(uint32_t N, bool crop) { return ".emosaic_" + std::to_string(N) + "to1" + (crop ? "_cropped" : ""); }
 
 // ---- cache ------------------------------------------------------------------------------------------

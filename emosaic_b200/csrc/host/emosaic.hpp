@@ -9,6 +9,7 @@
 //   render_nto1 / render_random   src/mosaic/rendering.rs:124-230, :418-440
 //   tint                          src/main.rs:447-478
 //   adjust_dims, cache file name  src/main.rs:567-601
+//   resize (Lanczos3), prepare_view / prepare_tile / rotate   src/main.rs:595, tiles/utils.rs:63-264
 //   TileSet (de)serialisation     tiles/tileset.rs:28-75, tiles/tile.rs:38-65 (bincode 1.3.3 defaults)
 //   RenderStats summarise/render  src/mosaic/stats.rs:87-195
 // Where the reference panics or exits, these throw emosaic::Error carrying the status code and message.
@@ -118,6 +119,15 @@ uint8_t tint_alpha(double tint_opacity);  // main.rs:449
 
 // ---- main.rs:567-601 --------------------------------------------------------------------------------
 std::pair<uint32_t, uint32_t> adjust_dims(uint32_t w, uint32_t h, uint32_t downsample, uint32_t dim);
+
+// ---- image 0.25.2 imageops::resize(.., Lanczos3) and prepare_tile (tiles/utils.rs:63-264) ---------------
+struct View { uint32_t x = 0, y = 0, w = 0, h = 0; };
+Image resize_lanczos3(Context &ctx, const Image &img, uint32_t nw, uint32_t nh, std::optional<View> view = std::nullopt);  // emo_resize
+Image resize_source(Context &ctx, const Image &original, uint32_t downsample, uint32_t dim);  // main.rs:567-595
+uint32_t most_common_value(const std::vector<uint32_t> &values);                              // utils.rs:262-273 (ties: smallest)
+View prepare_view(const Image &img, uint32_t tile_size, bool crop);                           // utils.rs:93-186
+Image rotate(const Image &img, uint32_t orientation);                                         // utils.rs:248-264
+Image prepare_tile(Context &ctx, const Image &decoded, uint32_t tile_size, bool crop, uint32_t orientation = 1);  // utils.rs:63-196
 std::string cache_file_name(uint32_t N, bool crop);
 
 // ---- cache (bincode 1.3.3 defaults) -----------------------------------------------------------------

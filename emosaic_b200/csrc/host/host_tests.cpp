@@ -146,6 +146,29 @@ int main(int argc, char **argv) {
         write_ppm("/tmp/emosaic_host_test.ppm", im);
         CHECK(read_image("/tmp/emosaic_host_test.ppm") == im);
     });
+    // tiles/utils.rs:284-289 (test_most_common_value) + the trim view / rotation bookkeeping of prepare_tile (:93-186, :248-264)
+    run("test_most_common_value / prepare_view / rotate", [] {
+        CHECK(most_common_value({1, 2, 2, 3, 3, 3, 4}) == 3);
+        CHECK(most_common_value({}) == 0 && most_common_value({9, 4, 9, 4}) == 4);
+        Image img(60, 40, 3);  // white frame: 5 left, 3 right, 4 top, 6 bottom
+        for (uint32_t y = 0; y < 40; y++)
+            for (uint32_t x = 0; x < 60; x++) memset(img.pixel(x, y), (x >= 5 && x < 57 && y >= 4 && y < 34) ? (int)((x * 7 + y * 3) % 200) : 255, 3);
+        const View v = prepare_view(img, 8, false);  // [first, last): the last non-white column / row is left out
+        CHECK(v.x == 5 && v.y == 4 && v.w == 51 && v.h == 29);
+        const View c = prepare_view(img, 8, true);
+        CHECK(c.w == 29 && c.h == 29 && c.x == 5 + 11 && c.y == 4);
+        Image white(20, 20, 3);
+        memset(white.data.data(), 255, white.data.size());
+        CHECK(throws_with([&] { prepare_view(white, 8, false); }, "assertion failed: first_non_white_col < last_non_white_col"));
+        CHECK(throws_with([&] { prepare_view(Image(30, 7, 3), 8, false); }, "smaller than the tile size"));
+        Image a(3, 2, 3);
+        for (size_t i = 0; i < a.data.size(); i++) a.data[i] = (uint8_t)i;
+        CHECK(rotate(a, 1) == a && rotate(rotate(a, 6), 8) == a && rotate(rotate(a, 3), 3) == a && rotate(rotate(a, 7), 7) == a);
+        const Image r6 = rotate(a, 6);  // clockwise: top-left goes to top-right
+        CHECK(r6.width == 2 && r6.height == 3 && !memcmp(r6.pixel(1, 0), a.pixel(0, 0), 3) && !memcmp(r6.pixel(0, 0), a.pixel(0, 1), 3));
+        const Image r5 = rotate(a, 5);  // transpose
+        CHECK(!memcmp(r5.pixel(1, 2), a.pixel(2, 1), 3));
+    });
     if (cpu_only) {
         printf("%s (%d failures, cpu-only subset)\n", failures ? "FAILED" : "OK", failures);
         return failures ? 1 : 0;
@@ -273,6 +296,25 @@ int main(int argc, char **argv) {
             RenderResult r = render_nto1(ctx, src, one, 4, false, std::nullopt, 0.5);
             CHECK(r.image.channels == 4 && r.image.pixel(2, 1)[0] == want[k] && r.image.pixel(0, 0)[3] == 255);
         }
+    });
+    // image 0.25.2 imageops::resize(Lanczos3) through emo_resize (main.rs:595, utils.rs:188-189) and utils.rs:291-299
+    run("test_resize / test_prepare_tile", [&] {
+        Image flat(131, 97, 3);
+        for (size_t k = 0; k < flat.data.size(); k += 3) { flat.data[k] = 7; flat.data[k + 1] = 200; flat.data[k + 2] = 255; }
+        const Image small = resize_lanczos3(ctx, flat, 16, 12);
+        bool same = small.width == 16 && small.height == 12;
+        for (size_t k = 0; k < small.data.size(); k += 3) same = same && small.data[k] == 7 && small.data[k + 1] == 200 && small.data[k + 2] == 255;
+        CHECK(same);  // normalised weights keep a flat image flat
+        Image img(45, 37, 3);
+        uint32_t seed = 99;
+        for (auto &v : img.data) { seed = seed * 1664525u + 1013904223u; v = (uint8_t)((seed >> 24) % 230); }
+        CHECK(resize_lanczos3(ctx, img, 45, 37) == img);  // same dimensions: copy (sample.rs resize())
+        const Image src = resize_source(ctx, img, 1, 2);  // 45 x 37 -> 44 x 36
+        CHECK(src.width == 44 && src.height == 36);
+        const Image tile = prepare_tile(ctx, img, 32, true);  // utils.rs:291-299: prepare_tile(.., 32, true) is 32 x 32
+        CHECK(tile.width == 32 && tile.height == 32);
+        CHECK(prepare_tile(ctx, img, 32, true, 6) == rotate(tile, 6));
+        CHECK(throws_with([&] { resize_lanczos3(ctx, img, 8, 8, View{40, 0, 10, 10}); }, "extends beyond"));
     });
     printf("%s (%d failures)\n", failures ? "FAILED" : "OK", failures);
     return failures ? 1 : 0;

@@ -78,6 +78,22 @@ int emo_host_free(emo_ctx *ctx, void *p);
 int emo_copy_h2d(emo_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
 int emo_copy_d2h(emo_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */
 
+/* ---- (0) Lanczos3 resize --------------------------------------------------------------------
+ * Replaces image 0.25.2 imageops::resize(view, nw, nh, FilterType::Lanczos3) at its two call sites
+ * on the path: the source image before matching (src/main.rs:595, after the dimension rule
+ * main.rs:567-587) and the photo -> tile resize of prepare_tile (src/mosaic/tiles/utils.rs:188-189,
+ * on the view left by the white-border trim / centre-square crop, utils.rs:93-186).
+ * images [n, img_h, img_w, 3]; every image of the batch is cropped to the view (x0, y0, cw, ch) and
+ * resized to out [n, nh, nw, 3].  Bit-exact restatement of the crate's two-pass f32 algorithm
+ * (vertical_sample into f32, horizontal_sample with clamp + round half away from zero, every tap one
+ * f32 multiply and one f32 add in ascending order); equal dimensions copy, as resize() does.  The tap
+ * weights (O(nw + nh) values, libm sinf like f32::sin) are prepared on the host side of the library,
+ * all per-pixel arithmetic runs on the GPU.  Limits: rows <= 65535. */
+int emo_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0,
+               uint32_t y0, uint32_t cw, uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out);
+int emo_resize_dev(emo_ctx *ctx, const uint8_t *images_dev, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0,
+                   uint32_t y0, uint32_t cw, uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out_dev);
+
 /* ---- (1) tile analysis ------------------------------------------------------------------
  * Replaces analyse::<N>() (src/mosaic/analysis.rs:5-20) + average_color()
  * (src/mosaic/color.rs:14-42) looped over the library (src/main.rs:786-794).

@@ -239,3 +239,40 @@ def cache_serialize(colors, idx, dates, paths) -> bytes:
                                   d_arr, p_arr, buf, C.c_uint64(need))
     assert n == need
     return bytes(buf)
+
+
+def resize_lanczos3(img, nw, nh, view=None):
+    """image 0.25.2 imageops::resize(view, nw, nh, Lanczos3) — main.rs:595, tiles/utils.rs:188-189.
+    img [H,W,3]; view = (x0, y0, cw, ch) or None for the whole image -> [nh,nw,3]."""
+    img = _u8(img)
+    H, W = img.shape[:2]
+    x0, y0, cw, ch = view if view is not None else (0, 0, W, H)
+    out = np.zeros((nh, nw, 3), np.uint8)
+    rc = lib().orc_resize_lanczos3(_p(img), C.c_uint32(W), C.c_uint32(H), C.c_uint32(x0), C.c_uint32(y0), C.c_uint32(cw),
+                                   C.c_uint32(ch), C.c_uint32(nw), C.c_uint32(nh), _p(out))
+    if rc:
+        raise ValueError(ERRORS.get(rc, str(rc)))
+    return out
+
+
+def resize_axis(n_in, n_out):
+    """Taps of one axis: (left [out], cnt [out], weights [out, max cnt] f32, zero beyond cnt)."""
+    pitch = lib().orc_resize_axis(C.c_uint32(n_in), C.c_uint32(n_out), None, None, None, C.c_uint32(0))
+    left = np.zeros(n_out, np.uint32)
+    cnt = np.zeros(n_out, np.uint32)
+    ws = np.zeros((n_out, pitch), np.float32)
+    lib().orc_resize_axis(C.c_uint32(n_in), C.c_uint32(n_out), _p(left, u32p), _p(cnt, u32p),
+                          ws.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(pitch))
+    return left, cnt, ws
+
+
+def prepare_view(img, tile_size, crop):
+    """tiles/utils.rs:93-186: the (x0, y0, w, h) view prepare_tile resizes (white-border trim by the mode of the
+    per-row / per-column first and last non-white positions, then the centred square when crop)."""
+    img = _u8(img)
+    H, W = img.shape[:2]
+    v = (C.c_uint32 * 4)()
+    rc = lib().orc_prepare_view(_p(img), C.c_uint32(W), C.c_uint32(H), C.c_uint32(tile_size), C.c_int(int(bool(crop))), v)
+    if rc:
+        raise ValueError("prepare_tile: image smaller than the tile size, or no non-white interior (utils.rs:99-106, :157-158)")
+    return tuple(int(x) for x in v)

@@ -490,3 +490,162 @@ int64_t orc_cache_serialize(const uint8_t *colors, uint32_t T, uint32_t N, const
     for (uint32_t t = 0; t < T; t++) { uint64_t l = strlen(paths[t]); put_u64(&p, l); memcpy(p, paths[t], l); p += l; }
     return (int64_t)(p - buf);
 }
+
+/* ---- image 0.25.2 imageops::resize(view, nw, nh, FilterType::Lanczos3) -----------------------
+ * Call sites on the path: src/main.rs:595 (the source image before matching) and
+ * tiles/utils.rs:188-189 (prepare_tile, on the trimmed / centre-cropped view).  The crate source
+ * is not under /root/reference; restated from the published algorithm of the pinned version
+ * (imageops/sample.rs: vertical_sample into an f32 image, then horizontal_sample with clamp +
+ * round-to-nearest; weights normalised before use; sinc via f32 sin).  PARITY UNPINNED: no
+ * reference test or golden vector touches a resize.
+ *   - same dimensions: plain copy (sample.rs resize(): "(nwidth, nheight) == image.dimensions()")
+ *   - ratio = in / out (f32); sratio = max(ratio, 1); support = 3 * sratio
+ *   - centre c = (o + 0.5) * ratio; left = clamp(floor(c - support), 0, in - 1);
+ *     right = clamp(ceil(c + support), left + 1, in); w_i = lanczos3((i - (c - 0.5)) / sratio);
+ *     w_i /= sum(w)  (sum accumulated left to right in f32)
+ *   - accumulation t += px * w_i, one f32 multiply and one f32 add per tap (Rust never contracts)
+ * f32::sin is the platform libm's sinf, as it is for a Linux build of the reference. */
+static float orc_sinc(float t) {
+    float a = t * 3.14159274101257324f; /* f32::consts::PI */
+    return t == 0.0f ? 1.0f : sinf(a) / a;
+}
+static float orc_lanczos3(float x) { return fabsf(x) < 3.0f ? orc_sinc(x) * orc_sinc(x / 3.0f) : 0.0f; }
+
+/* Taps of one axis.  left/cnt: [out]; ws: [out][pitch] (pitch >= every cnt).  Returns the largest cnt;
+ * with ws == NULL only counts. */
+uint32_t orc_resize_axis(uint32_t in, uint32_t out, uint32_t *left, uint32_t *cnt, float *ws, uint32_t pitch) {
+    float ratio = (float)in / (float)out;
+    float sratio = ratio < 1.0f ? 1.0f : ratio;
+    float support = 3.0f * sratio;
+    uint32_t maxc = 0;
+    for (uint32_t o = 0; o < out; o++) {
+        float c = ((float)o + 0.5f) * ratio;
+        int64_t l = (int64_t)floorf(c - support);
+        if (l < 0) l = 0;
+        if (l > (int64_t)in - 1) l = (int64_t)in - 1;
+        int64_t r = (int64_t)ceilf(c + support);
+        if (r < l + 1) r = l + 1;
+        if (r > (int64_t)in) r = (int64_t)in;
+        c = c - 0.5f;
+        uint32_t n = (uint32_t)(r - l);
+        if (n > maxc) maxc = n;
+        if (left) left[o] = (uint32_t)l;
+        if (cnt) cnt[o] = n;
+        if (ws) {
+            float sum = 0.0f;
+            float *w = ws + (size_t)o * pitch;
+            for (uint32_t i = 0; i < n; i++) {
+                w[i] = orc_lanczos3(((float)(l + i) - c) / sratio);
+                sum += w[i];
+            }
+            for (uint32_t i = 0; i < n; i++) w[i] /= sum;
+        }
+    }
+    return maxc;
+}
+
+/* img [img_h, img_w, 3]; view (x0, y0, cw, ch) -> out [nh, nw, 3]. */
+int orc_resize_lanczos3(const uint8_t *img, uint32_t img_w, uint32_t img_h, uint32_t x0, uint32_t y0, uint32_t cw,
+                        uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out) {
+    if (x0 + (uint64_t)cw > img_w || y0 + (uint64_t)ch > img_h) return ORC_ERR_ARG;
+    if (nw == 0 || nh == 0) return ORC_OK;
+    if (cw == 0 || ch == 0) { memset(out, 0, (size_t)nw * nh * 3); return ORC_OK; } /* "nothing to sample from" */
+    if (nw == cw && nh == ch) {
+        for (uint32_t y = 0; y < ch; y++)
+            memcpy(out + (size_t)y * cw * 3, img + ((size_t)(y0 + y) * img_w + x0) * 3, (size_t)cw * 3);
+        return ORC_OK;
+    }
+    uint32_t pv = orc_resize_axis(ch, nh, NULL, NULL, NULL, 0), ph = orc_resize_axis(cw, nw, NULL, NULL, NULL, 0);
+    uint32_t *lv = malloc(sizeof(uint32_t) * nh), *cv = malloc(sizeof(uint32_t) * nh);
+    uint32_t *lh = malloc(sizeof(uint32_t) * nw), *chn = malloc(sizeof(uint32_t) * nw);
+    float *wv = malloc(sizeof(float) * (size_t)nh * pv), *wh = malloc(sizeof(float) * (size_t)nw * ph);
+    float *tmp = malloc(sizeof(float) * (size_t)nh * cw * 3);
+    if (!lv || !cv || !lh || !chn || !wv || !wh || !tmp) { free(lv); free(cv); free(lh); free(chn); free(wv); free(wh); free(tmp); return ORC_ERR_ARG; }
+    orc_resize_axis(ch, nh, lv, cv, wv, pv);
+    orc_resize_axis(cw, nw, lh, chn, wh, ph);
+    /* vertical_sample: u8 view -> f32 [nh, cw, 3], no clamping or rounding */
+    #pragma omp parallel for schedule(static)
+    for (int64_t oy = 0; oy < (int64_t)nh; oy++) {
+        const float *w = wv + (size_t)oy * pv;
+        for (uint32_t x = 0; x < cw; x++)
+            for (uint32_t c = 0; c < 3; c++) {
+                float t = 0.0f;
+                for (uint32_t i = 0; i < cv[oy]; i++) {
+                    float p = (float)img[((size_t)(y0 + lv[oy] + i) * img_w + x0 + x) * 3 + c];
+                    float m = p * w[i];
+                    t = t + m;
+                }
+                tmp[((size_t)oy * cw + x) * 3 + c] = t;
+            }
+    }
+    /* horizontal_sample: f32 -> u8 with clamp(t, 0, 255) and FloatNearest (f32::round, half away from zero) */
+    #pragma omp parallel for schedule(static)
+    for (int64_t y = 0; y < (int64_t)nh; y++)
+        for (uint32_t ox = 0; ox < nw; ox++) {
+            const float *w = wh + (size_t)ox * ph;
+            for (uint32_t c = 0; c < 3; c++) {
+                float t = 0.0f;
+                for (uint32_t i = 0; i < chn[ox]; i++) {
+                    float m = tmp[((size_t)y * cw + lh[ox] + i) * 3 + c] * w[i];
+                    t = t + m;
+                }
+                if (t < 0.0f) t = 0.0f; else if (t > 255.0f) t = 255.0f;
+                out[((size_t)y * nw + ox) * 3 + c] = (uint8_t)roundf(t);
+            }
+        }
+    free(lv); free(cv); free(lh); free(chn); free(wv); free(wh); free(tmp);
+    return ORC_OK;
+}
+
+/* ---- tiles/utils.rs:93-186: the view prepare_tile resizes ------------------------------------
+ * White = every channel > 240 (utils.rs:94).  Per row the first / last non-white column, per column the
+ * first / last non-white row; the MODE of each list (rows/columns that are entirely white left out) bounds
+ * the view; `crop` then takes the centred largest square.  most_common_value (utils.rs:198-213) counts in a
+ * HashMap and takes max_by_key, whose winner among equally frequent values depends on the hash order; the
+ * canonical rule here is the smallest such value (PARITY UNPINNED for that tie).  The view is
+ * [first, last) on both axes: the last non-white column / row itself is left out (utils.rs:160-161).
+ * Returns ORC_ERR_ARG where the reference asserts or errors (image smaller than the tile; first >= last, which
+ * includes the all-white image: the mode of an empty list is 0). */
+static int64_t mode_u32(const uint32_t *v, uint32_t n, uint32_t skip, uint32_t range) {
+    uint32_t *hist = calloc((size_t)range + 1, sizeof(uint32_t));
+    int64_t best = 0; uint32_t bc = 0; /* empty iterator: unwrap_or((0, 0)).0 */
+    if (!hist) return -1;
+    for (uint32_t i = 0; i < n; i++) if (v[i] != skip) hist[v[i]]++;
+    for (uint32_t x = 0; x <= range; x++) if (hist[x] > bc) { bc = hist[x]; best = x; }
+    free(hist);
+    return best;
+}
+int orc_prepare_view(const uint8_t *img, uint32_t w, uint32_t h, uint32_t tile_size, int crop, uint32_t view[4]) {
+    if (w < tile_size || h < tile_size) return ORC_ERR_ARG; /* utils.rs:99-106 DimensionError */
+    uint32_t *fl = malloc(sizeof(uint32_t) * h), *fr = malloc(sizeof(uint32_t) * h);
+    uint32_t *ft = malloc(sizeof(uint32_t) * w), *fb = malloc(sizeof(uint32_t) * w);
+    #define ORC_WHITE(x, y) (img[((size_t)(y) * w + (x)) * 3] > 240 && img[((size_t)(y) * w + (x)) * 3 + 1] > 240 && img[((size_t)(y) * w + (x)) * 3 + 2] > 240)
+    for (uint32_t y = 0; y < h; y++) {
+        uint32_t x = 0;
+        while (x < w && ORC_WHITE(x, y)) x++;
+        fl[y] = x;                       /* unwrap_or(w) */
+        uint32_t r = 0;                  /* (fl..w).rev().find(non-white).unwrap_or(0) */
+        for (uint32_t k = w; k > fl[y]; k--) if (!ORC_WHITE(k - 1, y)) { r = k - 1; break; }
+        fr[y] = r;
+    }
+    for (uint32_t x = 0; x < w; x++) {
+        uint32_t y = 0;
+        while (y < h && ORC_WHITE(x, y)) y++;
+        ft[x] = y;
+        uint32_t r = 0;
+        for (uint32_t k = h; k > ft[x]; k--) if (!ORC_WHITE(x, k - 1)) { r = k - 1; break; }
+        fb[x] = r;
+    }
+    #undef ORC_WHITE
+    int64_t c0 = mode_u32(fl, h, w, w), c1 = mode_u32(fr, h, 0, w), r0 = mode_u32(ft, w, h, h), r1 = mode_u32(fb, w, 0, h);
+    free(fl); free(fr); free(ft); free(fb);
+    if (c0 < 0 || c1 < 0 || r0 < 0 || r1 < 0) return ORC_ERR_ARG; /* out of memory */
+    if (!(c0 < c1) || !(r0 < r1)) return ORC_ERR_ARG;              /* utils.rs:157-158 asserts */
+    uint32_t vw = (uint32_t)(c1 - c0), vh = (uint32_t)(r1 - r0), vx = (uint32_t)c0, vy = (uint32_t)r0;
+    if (crop) { /* utils.rs:170-182 */
+        uint32_t size = vw < vh ? vw : vh;
+        vx += (vw - size) / 2; vy += (vh - size) / 2; vw = vh = size;
+    }
+    view[0] = vx; view[1] = vy; view[2] = vw; view[3] = vh;
+    return ORC_OK;
+}

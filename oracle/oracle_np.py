@@ -231,3 +231,103 @@ def no_repeat_assign_literal(colors: np.ndarray, src: np.ndarray):
             keys = [-m[1][-1][0] for m in matches]                   # ascending view of the descending vector
             matches.insert(bisect.bisect_right(keys, -near[-1][0]), (n, near))
     return item, dist
+
+
+# ---- image 0.25.2 imageops::resize(.., Lanczos3): main.rs:595, tiles/utils.rs:188-189 ------------------------
+def _sinf(x: np.float32) -> np.float32:
+    """f32::sin = the platform libm's sinf (numpy's own float32 sin is a different implementation)."""
+    import ctypes
+    import ctypes.util
+    global _LIBM
+    try:
+        _LIBM
+    except NameError:
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _LIBM.sinf.restype = ctypes.c_float
+        _LIBM.sinf.argtypes = [ctypes.c_float]
+    return np.float32(_LIBM.sinf(float(x)))
+
+
+def _lanczos3(x: np.float32) -> np.float32:
+    f = np.float32
+
+    def sinc(t):
+        a = f(t * f(np.pi))
+        return f(1.0) if t == 0 else f(_sinf(a) / a)
+
+    return f(sinc(x) * sinc(f(x / f(3.0)))) if abs(x) < 3.0 else f(0.0)
+
+
+def resize_axis(n_in: int, n_out: int):
+    """sample.rs horizontal_sample / vertical_sample tap set-up: per output index (left, normalised f32 weights)."""
+    f = np.float32
+    ratio = f(f(n_in) / f(n_out))
+    sratio = f(1.0) if ratio < 1 else ratio
+    support = f(f(3.0) * sratio)
+    taps = []
+    for o in range(n_out):
+        c = f(f(f(o) + f(0.5)) * ratio)
+        left = min(max(int(np.floor(f(c - support))), 0), n_in - 1)
+        right = min(max(int(np.ceil(f(c + support))), left + 1), n_in)
+        c = f(c - f(0.5))
+        ws = [_lanczos3(f(f(f(i) - c) / sratio)) for i in range(left, right)]
+        s = f(0.0)
+        for w in ws:
+            s = f(s + w)
+        taps.append((left, np.array([f(w / s) for w in ws], np.float32)))
+    return taps
+
+
+def resize_lanczos3(img: np.ndarray, nw: int, nh: int) -> np.ndarray:
+    """resize(): vertical_sample into f32, then horizontal_sample with clamp and round (half away from zero)."""
+    h, w = img.shape[:2]
+    if (nw, nh) == (w, h):
+        return img.copy()
+    tmp = np.zeros((nh, w, 3), np.float32)
+    for oy, (left, ws) in enumerate(resize_axis(h, nh)):
+        t = np.zeros((w, 3), np.float32)
+        for i, wt in enumerate(ws):
+            t = t + img[left + i].astype(np.float32) * wt  # two separately rounded f32 operations
+        tmp[oy] = t
+    out = np.zeros((nh, nw, 3), np.uint8)
+    for ox, (left, ws) in enumerate(resize_axis(w, nw)):
+        t = np.zeros((nh, 3), np.float32)
+        for i, wt in enumerate(ws):
+            t = t + tmp[:, left + i] * wt
+        t = np.clip(t, np.float32(0), np.float32(255))
+        out[:, ox] = np.where(t - np.floor(t) >= 0.5, np.floor(t) + 1, np.floor(t)).astype(np.uint8)  # t >= 0: round half up
+    return out
+
+
+def prepare_view(img: np.ndarray, tile_size: int, crop: bool):
+    """tiles/utils.rs:93-186 with the smallest value winning a tie of most_common_value."""
+    h, w = img.shape[:2]
+    if w < tile_size or h < tile_size:
+        raise ValueError("DimensionError")
+    nonwhite = ~((img[..., 0] > 240) & (img[..., 1] > 240) & (img[..., 2] > 240))
+
+    def first_last(m):  # m [lines, n]: per line first non-white (n if none) and last non-white (0 if none)
+        n = m.shape[1]
+        anyv = m.any(axis=1)
+        first = np.where(anyv, m.argmax(axis=1), n)
+        last = np.where(anyv, n - 1 - m[:, ::-1].argmax(axis=1), 0)
+        return first, last
+
+    def mode(v, skip):
+        v = v[v != skip]
+        if v.size == 0:
+            return 0
+        vals, counts = np.unique(v, return_counts=True)
+        return int(vals[counts.argmax()])  # np.unique sorts: the first maximum is the smallest value
+
+    fl, fr = first_last(nonwhite)
+    ft, fb = first_last(nonwhite.T)
+    c0, c1, r0, r1 = mode(fl, w), mode(fr, 0), mode(ft, h), mode(fb, 0)
+    assert c0 < c1 and r0 < r1
+    vw, vh, vx, vy = c1 - c0, r1 - r0, c0, r0
+    if crop:
+        size = min(vw, vh)
+        vx += (vw - size) // 2
+        vy += (vh - size) // 2
+        vw = vh = size
+    return vx, vy, vw, vh

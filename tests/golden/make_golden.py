@@ -78,3 +78,16 @@ if __name__ == "__main__":
     open(os.path.join(HERE, "cache_4to1.bin"), "wb").write(blob)
     np.savez_compressed(os.path.join(HERE, "cache_4to1_meta.npz"), colors=ccol, paths=np.array(cpaths), dates=np.array([d or "" for d in cdates]))
     print("cache_4to1.bin", len(blob), "bytes")
+    # Lanczos3 resize (image 0.25.2 imageops::resize; main.rs:595, tiles/utils.rs:188-189): source-style near-identity
+    # resizes, a downsample by 2, a photo -> tile reduction with a view, an upscale
+    rng = np.random.default_rng(2024)
+    yy, xx = np.mgrid[0:97, 0:131]
+    photo = np.stack([(np.sin(xx / 9.0) * 100 + 128), (np.cos(yy / 7.0) * 90 + 120), ((xx * yy) % 256)], -1)
+    photo = np.clip(photo + rng.integers(-20, 21, photo.shape), 0, 255).astype(np.uint8)
+    rcases = [(photo, (0, 0, 131, 97), 130, 96), (photo, (0, 0, 131, 97), 65, 48), (photo, (7, 5, 88, 88), 16, 16),
+              (photo[:20, :24], (0, 0, 24, 20), 61, 47), (rng.integers(0, 256, (33, 29, 3), dtype=np.uint8), (1, 2, 27, 30), 27, 29)]
+    d = {"cases": len(rcases)}
+    for k, (img, view, nw, nh) in enumerate(rcases):
+        d[f"img{k}"], d[f"view{k}"], d[f"out{k}"] = img, np.array(view), oracle.resize_lanczos3(img, nw, nh, view)
+    np.savez_compressed(os.path.join(HERE, "resize_lanczos3.npz"), **d)
+    print("resize_lanczos3", len(rcases), "cases")

@@ -1,5 +1,5 @@
 """The reference-shaped command line end to end on the GPU: cache build (-f), cache reuse, 1to1 / 4to1 / random,
-tint.  Decoded tiles are re-prepared on the host and the expected images come from the CPU oracle."""
+tint.  The expected tiles (trim view, crop, Lanczos3 resize) and images come from the CPU oracle."""
 import os
 
 import numpy as np
@@ -22,6 +22,9 @@ def workdir(tmp_path_factory):
         base = rng.integers(0, 256, 3)
         img = np.clip(base + rng.integers(-30, 31, (40, 52, 3)), 0, 255).astype(np.uint8)
         img[:, :20] = np.clip(img[:, :20].astype(int) - 60, 0, 255)  # left/right asymmetry -> mirrored matches in 4to1
+        img = np.minimum(img, 225)                                    # nothing "white" (> 240 after JPEG ringing) inside ...
+        if i % 4 == 0:
+            img[:3 + i % 5] = img[-4:] = img[:, :5] = img[:, -2 - i % 3:] = 255   # ... but a white frame on some (utils.rs:93-167)
         p = tiles / ("sub" if i % 3 == 0 else "") / f"t{i:03d}.{'jpg' if i % 2 else 'jpeg'}"
         PIL.fromarray(img).save(p, quality=95)
     (tiles / "notes.txt").write_text("not an image")
@@ -31,10 +34,16 @@ def workdir(tmp_path_factory):
     return d, src
 
 
+def oracle_tile(path, ts, crop):
+    """prepare_tile (tiles/utils.rs:63-196) on the CPU oracle: decode, trim view / crop, Lanczos3 resize (no EXIF here)."""
+    img = np.asarray(PIL.open(path).convert("RGB"), dtype=np.uint8)
+    return oracle.resize_lanczos3(img, ts, ts, oracle.prepare_view(img, ts, crop))
+
+
 def expected(tiles_dir, src, dim, ts, crop):
     paths = cli.find_images(str(tiles_dir), {"jpg", "jpeg"})
-    px_an = np.stack([cli.prepare_tile(p, ts, crop) for p in paths])
-    px_rd = np.stack([cli.prepare_tile(p, ts, True) for p in paths])
+    px_an = np.stack([oracle_tile(p, ts, crop) for p in paths])
+    px_rd = np.stack([oracle_tile(p, ts, True) for p in paths])
     colors = oracle.analyse_tiles(px_an, dim * dim)
     item, dist = oracle.match(colors, src)
     return paths, colors, item, dist, px_an, px_rd
@@ -110,9 +119,9 @@ def test_cli_tint_uses_original_image_as_overlay(workdir):
                      "--downsample", "2", "-f"]) == 0
     from emosaic_b200 import api
     nw, nh = api.adjust_source_dims(src.shape[1], src.shape[0], 2, 1)
-    small = np.asarray(PIL.fromarray(src).resize((nw, nh), PIL.LANCZOS), dtype=np.uint8)
+    small = oracle.resize_lanczos3(src, nw, nh)  # main.rs:595
     paths = cli.find_images(str(d / "tiles"), {"jpg", "jpeg"})
-    px = np.stack([cli.prepare_tile(p, ts, True) for p in paths])
+    px = np.stack([oracle_tile(p, ts, True) for p in paths])
     colors = oracle.analyse_tiles(px, 1)
     item, _ = oracle.match(colors, small)
     want = oracle.tint(oracle.render(px, item), src, 127)

@@ -102,3 +102,47 @@ def _find_images(root):
 def _walk_order(root, paths):
     found = _find_images(root)
     return [found.index(p) for p in paths]
+
+
+@pytest.mark.gpu
+def test_cpp_cli_prepares_tiles_and_resizes_source(tmp_path):
+    """Tiles that are not tile_size x tile_size go through prepare_tile (trim view, crop, Lanczos3 on the GPU; tiles/utils.rs:63-196),
+    a 37 x 45 source in 4to1 mode is matched as its Lanczos3 resize to 36 x 44 (main.rs:567-595), --downsample 2, and the tint
+    overlay stays the image as opened (main.rs:447-466)."""
+    import oracle
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(31)
+    ts = 8
+    tiles_dir = tmp_path / "tiles"
+    tiles_dir.mkdir()
+    for i in range(30):
+        h, w = 30 + i % 7, 36 + i % 5
+        img = np.clip(rng.integers(0, 226, 3) + rng.integers(-25, 26, (h, w, 3)), 0, 225).astype(np.uint8)
+        img[:, : w // 3] //= 2
+        if i % 3 == 0:
+            img[:2] = img[-3:] = img[:, :4] = img[:, -1:] = 255            # white frame (utils.rs:93-167)
+        PIL.fromarray(img).save(tiles_dir / f"t{i:02d}.png")
+    src = rng.integers(0, 256, (37, 45, 3), dtype=np.uint8)
+    PIL.fromarray(src).save(tmp_path / "src.png")
+    found = _find_images(str(tiles_dir))
+
+    def tile(p, crop):
+        im = np.asarray(PIL.open(p).convert("RGB"), dtype=np.uint8)
+        return oracle.resize_lanczos3(im, ts, ts, oracle.prepare_view(im, ts, crop))
+
+    px_an, px_rd = np.stack([tile(p, False) for p in found]), np.stack([tile(p, True) for p in found])
+    colors = oracle.analyse_tiles(px_an, 4)
+    exe = _need("emosaic")
+    for downsample in (1, 2):
+        out = tmp_path / f"o{downsample}.png"
+        args = [exe, "-s", str(ts), "-o", str(out), str(tmp_path / "src.png"), "mosaic", str(tiles_dir), "-m", "2", "--extensions", "png",
+                "--downsample", str(downsample)]
+        r = subprocess.run(args + ["-f"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        nw, nh = oracle.adjust_dims(45, 37, downsample, 2)
+        assert f"Resizing source image from 45x37 to {nw}x{nh}" in r.stderr
+        item, _ = oracle.match(colors, oracle.resize_lanczos3(src, nw, nh))
+        assert (np.asarray(PIL.open(out)) == oracle.render(px_rd, item)).all()
+        r = subprocess.run(args + ["-t", "0.5"], capture_output=True, text=True, timeout=120)   # cache reuse + tint
+        assert r.returncode == 0 and "Reusing analysis cache" in r.stderr, r.stderr
+        assert (np.asarray(PIL.open(out)) == oracle.tint(oracle.render(px_rd, item), src, 127)).all()
