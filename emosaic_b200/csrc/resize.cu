@@ -15,12 +15,21 @@
 // exactly as f32::sin does in the reference) are computed on the host in resize_axis() and cached per geometry; all
 // O(pixels) arithmetic runs here.
 //
-//   resize_vertical_kernel<ALIGNED>: one thread per (image, output row, 4 consecutive bytes of the view row).  Rows of
-//     the view are read as 32-bit words when the geometry keeps them 4-byte aligned, bytes otherwise; a byte becomes an
-//     f32 exactly with PRMT (0x4B0000bb = 2^23 + b) and one FADD.  Writes one float4 per thread into tmp (row pitch
-//     padded to 4 floats).  The ~6x re-read of a source row by neighbouring output rows is served by L1/L2.
-//   resize_horizontal_kernel: one thread per (image, row, output pixel), three channel accumulators, weights stored
+//   resize_vertical_kernel<ALIGNED, TRANSPOSED>: one thread per (image, output row, 4 consecutive bytes of the view row).
+//     Rows of the view are read as 32-bit words: directly when the geometry keeps them 4-byte aligned, else as the two
+//     covering aligned words funnel-shifted by the row's phase.  The product
+//     f32(b) * w of a tap is formed WITHOUT converting the byte first: PRMT builds x = 0x4B0000bb = 2^23 + b (exact), and
+//     fma(x, w, -2^23 * w) = RN((2^23 + b) * w - 2^23 * w) = RN(b * w), because the FMA adds the exact 48-bit product to the
+//     exactly representable -2^23 * w and rounds once — the same single rounding as the reference's multiply.  The add that
+//     accumulates stays a separate FADD.  3 instructions per byte and tap (PRMT, FFMA, FADD) instead of 4.
+//     The ~6x re-read of a source row by neighbouring output rows is served by L1/L2.
+//   tmp layout: row-major [oy][x*3+c] (pitch padded to 4 floats, one float4 store per thread) when the image is about as
+//     wide as the output (source resize); TRANSPOSED [x*3+c][oy] for batches whose axes both shrink 8x or more (photo -> tile): there
+//     the windows of neighbouring output pixels lie far apart, so the horizontal pass runs with lanes along oy and reads
+//     every tap as one coalesced 128-byte row of the transposed image (the row-major layout costs 32 cache lines per load).
+//   resize_horizontal_kernel: one thread per (image, row, output pixel), lanes along the output row, weights stored
 //     tap-major ([tap][ox]) so that lanes read consecutive words.
+//   resize_horizontal_t_kernel: transposed input, one block per (image, output column), lanes along oy, weights uniform.
 //   resize_copy_kernel: the "(nwidth, nheight) == image.dimensions()" early return of resize() — a plain copy.
 #include <math.h>
 
@@ -81,17 +90,17 @@ static void resize_axis(uint32_t n_in, uint32_t n_out, emo_resize_axis &ax) {
 }
 
 // ---- device ---------------------------------------------------------------------------------------------------------------
-// exact u8 -> f32: PRMT builds 0x4B0000bb = 2^23 + b, one FADD removes the 2^23
+// RN(f32(byte K of v) * w) in one FFMA: x = 2^23 + b (PRMT), nbw = -2^23 * w (exact), fma(x, w, nbw) rounds b * w once
 template <int K>
-__device__ __forceinline__ float byte_f32(uint32_t v) {
-    return __fadd_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 | K)), -8388608.0f);
+__device__ __forceinline__ float byte_times(uint32_t v, float w, float nbw) {
+    return __fmaf_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 | K)), w, nbw);
 }
 
-template <bool ALIGNED>
+template <bool ALIGNED, bool TRANSPOSED>
 __global__ void __launch_bounds__(256)
 resize_vertical_kernel(const uint8_t *__restrict__ src, size_t img_bytes, uint32_t row_stride, size_t base_off, uint32_t row_bytes,
                        const uint32_t *__restrict__ left, const uint32_t *__restrict__ cnt, const float *__restrict__ ws,
-                       uint32_t wpitch, float *__restrict__ tmp, uint32_t tpitch, uint32_t nh, uint32_t n0) {
+                       uint32_t wpitch, float *__restrict__ tmp, uint32_t tpitch, uint32_t nh, uint32_t np, uint32_t n0) {
     const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (xb >= row_bytes) return;
     const uint32_t oy = blockIdx.y, n = blockIdx.z + n0;
@@ -104,28 +113,42 @@ resize_vertical_kernel(const uint8_t *__restrict__ src, size_t img_bytes, uint32
 #pragma unroll 4
         for (uint32_t i = 0; i < c; i++, p += row_stride) {
             const uint32_t v = __ldg((const uint32_t *)p);
-            const float wi = __ldg(w + i);
-            t0 = __fadd_rn(t0, __fmul_rn(byte_f32<0>(v), wi));
-            t1 = __fadd_rn(t1, __fmul_rn(byte_f32<1>(v), wi));
-            t2 = __fadd_rn(t2, __fmul_rn(byte_f32<2>(v), wi));
-            t3 = __fadd_rn(t3, __fmul_rn(byte_f32<3>(v), wi));
+            const float wi = __ldg(w + i), nbw = __fmul_rn(wi, -8388608.0f);
+            t0 = __fadd_rn(t0, byte_times<0>(v, wi, nbw));
+            t1 = __fadd_rn(t1, byte_times<1>(v, wi, nbw));
+            t2 = __fadd_rn(t2, byte_times<2>(v, wi, nbw));
+            t3 = __fadd_rn(t3, byte_times<3>(v, wi, nbw));
         }
     } else {
+        // rows that are not 4-byte aligned (the usual case when the width is not divisible: 3 * 4097 bytes per row): the two
+        // aligned words that cover the group, funnel-shifted by the row's phase.  An aligned word never straddles a page,
+        // and the upper word is only touched when it holds a byte of the view.
+        const uint32_t need = valid < 4 ? valid : 4;
 #pragma unroll 2
         for (uint32_t i = 0; i < c; i++, p += row_stride) {
-            uint32_t v = __ldg(p);
-            if (valid > 1) v |= (uint32_t)__ldg(p + 1) << 8;
-            if (valid > 2) v |= (uint32_t)__ldg(p + 2) << 16;
-            if (valid > 3) v |= (uint32_t)__ldg(p + 3) << 24;
-            const float wi = __ldg(w + i);
-            t0 = __fadd_rn(t0, __fmul_rn(byte_f32<0>(v), wi));
-            t1 = __fadd_rn(t1, __fmul_rn(byte_f32<1>(v), wi));
-            t2 = __fadd_rn(t2, __fmul_rn(byte_f32<2>(v), wi));
-            t3 = __fadd_rn(t3, __fmul_rn(byte_f32<3>(v), wi));
+            const uint32_t ph = (uint32_t)((uintptr_t)p & 3);
+            const uint32_t *q = (const uint32_t *)(p - ph);
+            const uint32_t lo = __ldg(q);
+            const uint32_t hi = ph + need > 4 ? __ldg(q + 1) : 0u;
+            const uint32_t v = __funnelshift_r(lo, hi, ph * 8);  // bytes beyond the view only feed the padding lanes of tmp
+            const float wi = __ldg(w + i), nbw = __fmul_rn(wi, -8388608.0f);
+            t0 = __fadd_rn(t0, byte_times<0>(v, wi, nbw));
+            t1 = __fadd_rn(t1, byte_times<1>(v, wi, nbw));
+            t2 = __fadd_rn(t2, byte_times<2>(v, wi, nbw));
+            t3 = __fadd_rn(t3, byte_times<3>(v, wi, nbw));
         }
     }
-    // tmp rows are padded to a multiple of 4 floats: the padding lanes of the last group hold sums of zero bytes
-    *(float4 *)(tmp + ((size_t)blockIdx.z * nh + oy) * tpitch + xb) = make_float4(t0, t1, t2, t3);
+    if (TRANSPOSED) {
+        // [x*3+c][oy], np floats per line; the padding lines of the last group (sums of zero bytes) exist in the buffer
+        float *o = tmp + ((size_t)blockIdx.z * tpitch + xb) * np + oy;
+        o[0] = t0;
+        o[np] = t1;
+        o[2 * (size_t)np] = t2;
+        o[3 * (size_t)np] = t3;
+    } else {
+        // rows are padded to a multiple of 4 floats: the padding lanes of the last group hold sums of zero bytes
+        *(float4 *)(tmp + ((size_t)blockIdx.z * nh + oy) * tpitch + xb) = make_float4(t0, t1, t2, t3);
+    }
 }
 
 __device__ __forceinline__ uint8_t clamp_round_u8(float t) {
@@ -153,6 +176,32 @@ resize_horizontal_kernel(const float *__restrict__ tmp, uint32_t tpitch, const u
         t2 = __fadd_rn(t2, __fmul_rn(__ldg(row + 3 * i + 2), wi));
     }
     uint8_t *o = out + (((size_t)n * nh + y) * nw + ox) * 3;
+    o[0] = clamp_round_u8(t0);
+    o[1] = clamp_round_u8(t1);
+    o[2] = clamp_round_u8(t2);
+}
+
+// Transposed intermediate [x*3+c][oy] (np floats per line): one block per (image, output column), lanes along oy, so a
+// tap is three coalesced loads and the weight is uniform across the block.
+__global__ void __launch_bounds__(128)
+resize_horizontal_t_kernel(const float *__restrict__ tmpT, uint32_t tpitch, uint32_t np, const uint32_t *__restrict__ left,
+                           const uint32_t *__restrict__ cnt, const float *__restrict__ ws, uint32_t wpitch, uint32_t nw, uint32_t nh,
+                           uint8_t *__restrict__ out, uint32_t n0) {
+    const uint32_t oy = blockIdx.y * blockDim.x + threadIdx.x;
+    if (oy >= nh) return;
+    const uint32_t ox = blockIdx.x, n = blockIdx.z + n0;
+    const uint32_t c = cnt[ox];
+    const float *__restrict__ col = tmpT + ((size_t)blockIdx.z * tpitch + (size_t)left[ox] * 3) * np + oy;
+    const float *__restrict__ w = ws + (size_t)ox * wpitch;
+    float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+#pragma unroll 4
+    for (uint32_t i = 0; i < c; i++, col += 3 * (size_t)np) {
+        const float wi = __ldg(w + i);
+        t0 = __fadd_rn(t0, __fmul_rn(__ldg(col), wi));
+        t1 = __fadd_rn(t1, __fmul_rn(__ldg(col + np), wi));
+        t2 = __fadd_rn(t2, __fmul_rn(__ldg(col + 2 * (size_t)np), wi));
+    }
+    uint8_t *o = out + (((size_t)n * nh + oy) * nw + ox) * 3;
     o[0] = clamp_round_u8(t0);
     o[1] = clamp_round_u8(t1);
     o[2] = clamp_round_u8(t2);
@@ -204,7 +253,7 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     if (st.h.n_in != cw || st.h.n_out != nw) { resize_axis(cw, nw, st.h); st.uploaded = false; }
     const uint32_t pv = st.v.pitch, ph = st.h.pitch;
     const size_t off_lv = 0, off_cv = off_lv + nh, off_lh = off_cv + nh, off_ch = off_lh + nw, off_wv = off_ch + nw,
-                 off_wh = off_wv + (size_t)nh * pv, words = off_wh + (size_t)ph * nw;
+                 off_wh = off_wv + (size_t)nh * pv, off_whr = off_wh + (size_t)ph * nw, words = off_whr + (size_t)ph * nw;
     int rc;
     if (!st.uploaded) {
         if ((rc = emo_ensure(ctx, (void **)&st.d_tab, &st.d_tab_cap, words * 4))) return rc;
@@ -214,19 +263,28 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
         memcpy(host.data() + off_lh, st.h.left.data(), (size_t)nw * 4);
         memcpy(host.data() + off_ch, st.h.cnt.data(), (size_t)nw * 4);
         memcpy(host.data() + off_wv, st.v.ws.data(), (size_t)nh * pv * 4);
-        float *wt = (float *)(host.data() + off_wh);
+        float *wt = (float *)(host.data() + off_wh);  // tap-major copy for the row-major horizontal kernel
         for (uint32_t o = 0; o < nw; o++)
             for (uint32_t i = 0; i < ph; i++) wt[(size_t)i * nw + o] = st.h.ws[(size_t)o * ph + i];
+        memcpy(host.data() + off_whr, st.h.ws.data(), (size_t)nw * ph * 4);
         // pageable source: the runtime stages it before returning, `host` may go out of scope
         EMO_CK(cudaMemcpyAsync(st.d_tab, host.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
         EMO_CK(cudaStreamSynchronize(ctx->stream));
         st.uploaded = true;
     }
     const uint32_t *d_lv = st.d_tab + off_lv, *d_cv = st.d_tab + off_cv, *d_lh = st.d_tab + off_lh, *d_ch = st.d_tab + off_ch;
-    const float *d_wv = (const float *)(st.d_tab + off_wv), *d_wh = (const float *)(st.d_tab + off_wh);
+    const float *d_wv = (const float *)(st.d_tab + off_wv), *d_wh = (const float *)(st.d_tab + off_wh),
+                *d_whr = (const float *)(st.d_tab + off_whr);
     const uint32_t tpitch = (row_bytes + 3) / 4 * 4;
+    // Transposed intermediate (see the header comment) for batches of photo -> tile reductions: both axes shrink 8x or more
+    // (48+ taps amortise the four scattered stores of the vertical pass), at least a warp of output rows, and enough outputs
+    // that the horizontal pass is throughput-bound.  Measured (tools/bench_resize.py, ncu launch lists under profiles/):
+    // 64 x 2048^2 -> 64^2 horizontal pass 615 -> 90 us; but 8192^2 -> 4096^2 (13 taps) 2.7x slower and a single
+    // 4000x3000 photo (4096 outputs, latency-bound, the row-major layout keeps a thread's taps in one L1 line) 1.3x slower.
+    const bool transposed = cw >= 8 * (uint64_t)nw && ch >= 8 * (uint64_t)nh && nh >= 32 && (uint64_t)n * nh * nw >= 65536;
+    const uint32_t np = (nh + 31) / 32 * 32;
     // images per pass: bounded by the f32 intermediate (<= 1 GiB) and the grid's z extent
-    const size_t tmp_per_img = (size_t)nh * tpitch * 4;
+    const size_t tmp_per_img = (size_t)(transposed ? np : nh) * tpitch * 4;
     uint32_t per_pass = (uint32_t)((1ull << 30) / tmp_per_img);
     if (per_pass < 1) per_pass = 1;
     if (per_pass > n) per_pass = n;
@@ -237,15 +295,24 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     for (uint32_t z0 = 0; z0 < n; z0 += per_pass) {
         const uint32_t nz = n - z0 < per_pass ? n - z0 : per_pass;
         const dim3 gv((groups + 255) / 256, nh, nz);
-        if (aligned)
-            resize_vertical_kernel<true><<<gv, 256, 0, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv,
-                                                                    d_wv, pv, st.tmp, tpitch, nh, z0);
-        else
-            resize_vertical_kernel<false><<<gv, 256, 0, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv,
-                                                                     d_wv, pv, st.tmp, tpitch, nh, z0);
+#define EMO_VERTICAL(A, T)                                                                                                         \
+    resize_vertical_kernel<A, T><<<gv, 256, 0, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv, d_wv, pv, \
+                                                             st.tmp, tpitch, nh, np, z0)
+        if (transposed) {
+            if (aligned) EMO_VERTICAL(true, true); else EMO_VERTICAL(false, true);
+        } else {
+            if (aligned) EMO_VERTICAL(true, false); else EMO_VERTICAL(false, false);
+        }
+#undef EMO_VERTICAL
         EMO_LAUNCH_CHECK(ctx);
-        resize_horizontal_kernel<<<dim3((nw + 127) / 128, nh, nz), 128, 0, ctx->stream>>>(st.tmp, tpitch, d_lh, d_ch, d_wh, nw, nh,
-                                                                                        out, z0);
+        if (transposed) {
+            const uint32_t bt = nh >= 128 ? 128 : (nh + 31) / 32 * 32;
+            resize_horizontal_t_kernel<<<dim3(nw, (nh + bt - 1) / bt, nz), bt, 0, ctx->stream>>>(st.tmp, tpitch, np, d_lh, d_ch, d_whr, ph,
+                                                                                               nw, nh, out, z0);
+        } else {
+            resize_horizontal_kernel<<<dim3((nw + 127) / 128, nh, nz), 128, 0, ctx->stream>>>(st.tmp, tpitch, d_lh, d_ch, d_wh, nw, nh,
+                                                                                            out, z0);
+        }
         EMO_LAUNCH_CHECK(ctx);
     }
     return EMO_OK;

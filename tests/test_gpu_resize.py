@@ -72,6 +72,19 @@ def test_resize_properties_large(ctx):
     assert (tiles[4] == ctx.resize(batch[4], 64, 64)).all() and (tiles[8] == oracle.resize_lanczos3(batch[8], 64, 64)).all()
 
 
+@pytest.mark.parametrize("n,h,w,view,ts", [(17, 512, 512, None, 64), (16, 515, 521, (3, 1, 512, 513), 64), (70, 300, 280, (0, 0, 280, 299), 32),
+                                           (33, 512, 512, (1, 0, 511, 512), 48)])
+def test_resize_tile_batches_transposed_path(ctx, n, h, w, view, ts):
+    """Batches of photo -> tile reductions (>= 8x on both axes, >= 65536 outputs) take the transposed intermediate
+    (resize.cu); aligned and unaligned rows, views, a tile size that is not a multiple of 32."""
+    rng = np.random.default_rng(n * 7 + ts)
+    imgs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    imgs[n // 2] = _photo(rng, h, w)
+    got = ctx.resize(imgs, ts, ts, view)
+    want = np.stack([oracle.resize_lanczos3(im, ts, ts, view) for im in imgs])
+    assert (got == want).all()
+
+
 def test_resize_device_pointers_unaligned_and_guarded(ctx):
     """Device-pointer entry: odd base addresses (byte path), canaries around the output."""
     torch = pytest.importorskip("torch")

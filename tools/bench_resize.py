@@ -1,5 +1,6 @@
-"""emo_resize (Lanczos3, image 0.25.2 bit-exact) throughput on a few geometries (run under gpurun).
-Reports per-kernel times through event marks around the two passes is not possible from outside; the whole call is timed."""
+"""emo_resize (Lanczos3, image 0.25.2 bit-exact) throughput on a few geometries (run under gpurun); the whole call (vertical +
+horizontal pass) is timed with CUDA events, the split per kernel comes from the ncu launch list (tools/summarise_ncu.py launches).
+usage: python tools/bench_resize.py [case index ...]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,7 +18,8 @@ CASES = [  # n, h, w, nh, nw
     (4096, 256, 256, 8, 8),
     (1, 1024, 1024, 4096, 4096),      # upscale
 ]
-for n, h, w, nh, nw in CASES:
+sel = [int(a) for a in sys.argv[1:]]
+for n, h, w, nh, nw in ([CASES[i] for i in sel] if sel else CASES):
     imgs = torch.randint(0, 256, (n * h * w * 3,), dtype=torch.uint8, device=dev)
     out = torch.empty(n * nh * nw * 3, dtype=torch.uint8, device=dev)
     fn = lambda: ctx.resize_dev(imgs.data_ptr(), n, w, h, None, nw, nh, out.data_ptr())
