@@ -15,15 +15,16 @@
 // exactly as f32::sin does in the reference) are computed on the host in resize_axis() and cached per geometry; all
 // O(pixels) arithmetic runs here.
 //
-//   resize_vertical_kernel<ALIGNED, TRANSPOSED>: one thread per (image, output row, 4 consecutive bytes of the view row).
-//     Rows of the view are read as 32-bit words: directly when the geometry keeps them 4-byte aligned, else as the two
-//     covering aligned words funnel-shifted by the row's phase.  The product
-//     f32(b) * w of a tap is formed WITHOUT converting the byte first: PRMT builds x = 0x4B0000bb = 2^23 + b (exact), and
-//     fma(x, w, -2^23 * w) = RN((2^23 + b) * w - 2^23 * w) = RN(b * w), because the FMA adds the exact 48-bit product to the
-//     exactly representable -2^23 * w and rounds once — the same single rounding as the reference's multiply.  The add that
-//     accumulates stays a separate FADD.  3 instructions per byte and tap (PRMT, FFMA, FADD) instead of 4.
-//     The ~6x re-read of a source row by neighbouring output rows is served by L1/L2.
-//   tmp layout: row-major [oy][x*3+c] (pitch padded to 4 floats, one float4 store per thread) when the image is about as
+//   resize_vertical_kernel<ALIGNED, TRANSPOSED>: one thread per (image, output row, 8 consecutive bytes of the view row).
+//     Rows of the view are read as one 64-bit word when the geometry keeps them 8-byte aligned, else as the two or three
+//     covering aligned 32-bit words funnel-shifted by the row's phase.  The product f32(b) * w of a tap is formed WITHOUT
+//     converting the byte first: PRMT builds x = 0x4B0000bb = 2^23 + b (exact), and fma(x, w, -2^23 * w) =
+//     RN((2^23 + b) * w - 2^23 * w) = RN(b * w), because the FMA adds the exact 48-bit product to the exactly representable
+//     -2^23 * w and rounds once — the same single rounding as the reference's multiply.  The add that accumulates stays
+//     a separate FADD: 3 instructions per byte and tap (PRMT, FFMA, FADD) instead of 4.  w and -2^23 * w come from the
+//     table as one 128-bit load per four taps each.  The kernel is issue-bound (ncu: 86 % of the issue slots, DRAM 14 %,
+//     L2 30 %): the ~6x re-read of a source row by neighbouring output rows is served by L1/L2 and is not the limiter.
+//   tmp layout: row-major [oy][x*3+c] (pitch padded to 8 floats, two float4 stores per thread) when the image is about as
 //     wide as the output (source resize); TRANSPOSED [x*3+c][oy] for batches whose axes both shrink 8x or more (photo -> tile): there
 //     the windows of neighbouring output pixels lie far apart, so the horizontal pass runs with lanes along oy and reads
 //     every tap as one coalesced 128-byte row of the transposed image (the row-major layout costs 32 cache lines per load).
@@ -96,58 +97,74 @@ __device__ __forceinline__ float byte_times(uint32_t v, float w, float nbw) {
     return __fmaf_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 | K)), w, nbw);
 }
 
+// one tap of one 4-byte group: t[k] += RN(byte_k * w), the multiply as the exact FFMA above, the add separate
+__device__ __forceinline__ void tap4(float *t, uint32_t v, float w, float nbw) {
+    t[0] = __fadd_rn(t[0], byte_times<0>(v, w, nbw));
+    t[1] = __fadd_rn(t[1], byte_times<1>(v, w, nbw));
+    t[2] = __fadd_rn(t[2], byte_times<2>(v, w, nbw));
+    t[3] = __fadd_rn(t[3], byte_times<3>(v, w, nbw));
+}
+
 template <bool ALIGNED, bool TRANSPOSED>
 __global__ void __launch_bounds__(256)
 resize_vertical_kernel(const uint8_t *__restrict__ src, size_t img_bytes, uint32_t row_stride, size_t base_off, uint32_t row_bytes,
                        const uint32_t *__restrict__ left, const uint32_t *__restrict__ cnt, const float *__restrict__ ws,
-                       uint32_t wpitch, float *__restrict__ tmp, uint32_t tpitch, uint32_t nh, uint32_t np, uint32_t n0) {
-    const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+                       const float *__restrict__ nbws, uint32_t wpitch, float *__restrict__ tmp, uint32_t tpitch, uint32_t nh,
+                       uint32_t np, uint32_t n0) {
+    const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (xb >= row_bytes) return;
     const uint32_t oy = blockIdx.y, n = blockIdx.z + n0;
     const uint32_t c = cnt[oy];
-    const float *__restrict__ w = ws + (size_t)oy * wpitch;
+    const float *__restrict__ w = ws + (size_t)oy * wpitch;      // wpitch is a multiple of 4: 16-byte aligned rows
+    const float *__restrict__ nb = nbws + (size_t)oy * wpitch;   // -2^23 * w
     const uint8_t *p = src + (size_t)n * img_bytes + base_off + (size_t)left[oy] * row_stride + xb;
     const uint32_t valid = row_bytes - xb;  // bytes of this thread's group that belong to the view (>= 1)
-    float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-    if (ALIGNED && valid >= 4) {
-#pragma unroll 4
-        for (uint32_t i = 0; i < c; i++, p += row_stride) {
-            const uint32_t v = __ldg((const uint32_t *)p);
-            const float wi = __ldg(w + i), nbw = __fmul_rn(wi, -8388608.0f);
-            t0 = __fadd_rn(t0, byte_times<0>(v, wi, nbw));
-            t1 = __fadd_rn(t1, byte_times<1>(v, wi, nbw));
-            t2 = __fadd_rn(t2, byte_times<2>(v, wi, nbw));
-            t3 = __fadd_rn(t3, byte_times<3>(v, wi, nbw));
+    float t[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (ALIGNED && valid >= 8) {
+        uint32_t i = 0;
+        for (; i + 4 <= c; i += 4) {
+            const float4 w4 = __ldg((const float4 *)(w + i)), n4 = __ldg((const float4 *)(nb + i));
+            const uint2 v0 = __ldg((const uint2 *)p), v1 = __ldg((const uint2 *)(p + row_stride)),
+                        v2 = __ldg((const uint2 *)(p + 2 * (size_t)row_stride)), v3 = __ldg((const uint2 *)(p + 3 * (size_t)row_stride));
+            p += 4 * (size_t)row_stride;
+            tap4(t, v0.x, w4.x, n4.x); tap4(t + 4, v0.y, w4.x, n4.x);
+            tap4(t, v1.x, w4.y, n4.y); tap4(t + 4, v1.y, w4.y, n4.y);
+            tap4(t, v2.x, w4.z, n4.z); tap4(t + 4, v2.y, w4.z, n4.z);
+            tap4(t, v3.x, w4.w, n4.w); tap4(t + 4, v3.y, w4.w, n4.w);
+        }
+        for (; i < c; i++, p += row_stride) {
+            const uint2 v = __ldg((const uint2 *)p);
+            const float wi = __ldg(w + i), ni = __ldg(nb + i);
+            tap4(t, v.x, wi, ni); tap4(t + 4, v.y, wi, ni);
         }
     } else {
-        // rows that are not 4-byte aligned (the usual case when the width is not divisible: 3 * 4097 bytes per row): the two
-        // aligned words that cover the group, funnel-shifted by the row's phase.  An aligned word never straddles a page,
-        // and the upper word is only touched when it holds a byte of the view.
-        const uint32_t need = valid < 4 ? valid : 4;
+        // rows that are not 8-byte aligned (the usual case when the width is not divisible: 3 * 4097 bytes per row): the
+        // aligned 32-bit words that cover the group, funnel-shifted by the row's phase.  An aligned word never straddles a
+        // page, and a word is only touched when it holds a byte of the view.
+        const uint32_t need = valid < 8 ? valid : 8;
 #pragma unroll 2
         for (uint32_t i = 0; i < c; i++, p += row_stride) {
             const uint32_t ph = (uint32_t)((uintptr_t)p & 3);
             const uint32_t *q = (const uint32_t *)(p - ph);
-            const uint32_t lo = __ldg(q);
-            const uint32_t hi = ph + need > 4 ? __ldg(q + 1) : 0u;
-            const uint32_t v = __funnelshift_r(lo, hi, ph * 8);  // bytes beyond the view only feed the padding lanes of tmp
-            const float wi = __ldg(w + i), nbw = __fmul_rn(wi, -8388608.0f);
-            t0 = __fadd_rn(t0, byte_times<0>(v, wi, nbw));
-            t1 = __fadd_rn(t1, byte_times<1>(v, wi, nbw));
-            t2 = __fadd_rn(t2, byte_times<2>(v, wi, nbw));
-            t3 = __fadd_rn(t3, byte_times<3>(v, wi, nbw));
+            const uint32_t a0 = __ldg(q);
+            const uint32_t a1 = ph + need > 4 ? __ldg(q + 1) : 0u;
+            const uint32_t a2 = ph + need > 8 ? __ldg(q + 2) : 0u;
+            const float wi = __ldg(w + i), ni = __ldg(nb + i);
+            // bytes beyond the view only feed the padding lanes of tmp
+            tap4(t, __funnelshift_r(a0, a1, ph * 8), wi, ni);
+            tap4(t + 4, __funnelshift_r(a1, a2, ph * 8), wi, ni);
         }
     }
     if (TRANSPOSED) {
-        // [x*3+c][oy], np floats per line; the padding lines of the last group (sums of zero bytes) exist in the buffer
+        // [x*3+c][oy], np floats per line; the padding lines of the last group (sums of bytes beyond the view) exist in the buffer
         float *o = tmp + ((size_t)blockIdx.z * tpitch + xb) * np + oy;
-        o[0] = t0;
-        o[np] = t1;
-        o[2 * (size_t)np] = t2;
-        o[3 * (size_t)np] = t3;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k * (size_t)np] = t[k];
     } else {
-        // rows are padded to a multiple of 4 floats: the padding lanes of the last group hold sums of zero bytes
-        *(float4 *)(tmp + ((size_t)blockIdx.z * nh + oy) * tpitch + xb) = make_float4(t0, t1, t2, t3);
+        // rows are padded to a multiple of 8 floats: the padding lanes of the last group are never read
+        float4 *o = (float4 *)(tmp + ((size_t)blockIdx.z * nh + oy) * tpitch + xb);
+        o[0] = make_float4(t[0], t[1], t[2], t[3]);
+        o[1] = make_float4(t[4], t[5], t[6], t[7]);
     }
 }
 
@@ -219,7 +236,7 @@ resize_copy_kernel(const uint8_t *__restrict__ src, size_t img_bytes, uint32_t r
 // ---- launcher -------------------------------------------------------------------------------------------------------------
 struct emo_resize_state {
     emo_resize_axis v, h;
-    uint32_t *d_tab = nullptr;  // device: left_v | cnt_v | left_h | cnt_h | ws_v [nh][pv] | ws_h transposed [ph][nw]
+    uint32_t *d_tab = nullptr;  // device: left_v | cnt_v | left_h | cnt_h | ws_v [nh][pv] | -2^23 ws_v | ws_h tap-major [ph][nw] | ws_h [nw][ph]
     size_t d_tab_cap = 0;
     bool uploaded = false;
     float *tmp = nullptr;
@@ -251,18 +268,27 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     emo_resize_state &st = *ctx->resize;
     if (st.v.n_in != ch || st.v.n_out != nh) { resize_axis(ch, nh, st.v); st.uploaded = false; }
     if (st.h.n_in != cw || st.h.n_out != nw) { resize_axis(cw, nw, st.h); st.uploaded = false; }
-    const uint32_t pv = st.v.pitch, ph = st.h.pitch;
-    const size_t off_lv = 0, off_cv = off_lv + nh, off_lh = off_cv + nh, off_ch = off_lh + nw, off_wv = off_ch + nw,
-                 off_wh = off_wv + (size_t)nh * pv, off_whr = off_wh + (size_t)ph * nw, words = off_whr + (size_t)ph * nw;
+    const uint32_t pv = (st.v.pitch + 3) / 4 * 4, ph = st.h.pitch;  // vertical weight rows padded for 128-bit loads
+    // every section starts on a 16-byte boundary
+    auto up4 = [](size_t x) { return (x + 3) / 4 * 4; };
+    const size_t off_lv = 0, off_cv = up4(off_lv + nh), off_lh = up4(off_cv + nh), off_ch = up4(off_lh + nw), off_wv = up4(off_ch + nw),
+                 off_nv = off_wv + (size_t)nh * pv, off_wh = off_nv + (size_t)nh * pv, off_whr = up4(off_wh + (size_t)ph * nw),
+                 words = off_whr + (size_t)ph * nw;
     int rc;
     if (!st.uploaded) {
         if ((rc = emo_ensure(ctx, (void **)&st.d_tab, &st.d_tab_cap, words * 4))) return rc;
-        std::vector<uint32_t> host(words);
+        std::vector<uint32_t> host(words, 0u);
         memcpy(host.data() + off_lv, st.v.left.data(), (size_t)nh * 4);
         memcpy(host.data() + off_cv, st.v.cnt.data(), (size_t)nh * 4);
         memcpy(host.data() + off_lh, st.h.left.data(), (size_t)nw * 4);
         memcpy(host.data() + off_ch, st.h.cnt.data(), (size_t)nw * 4);
-        memcpy(host.data() + off_wv, st.v.ws.data(), (size_t)nh * pv * 4);
+        float *wv = (float *)(host.data() + off_wv), *nv = (float *)(host.data() + off_nv);
+        for (uint32_t o = 0; o < nh; o++)
+            for (uint32_t i = 0; i < st.v.pitch; i++) {
+                const float wi = st.v.ws[(size_t)o * st.v.pitch + i];
+                wv[(size_t)o * pv + i] = wi;
+                nv[(size_t)o * pv + i] = wi * -8388608.0f;  // exact (a power of two), the addend of the kernel's FFMA
+            }
         float *wt = (float *)(host.data() + off_wh);  // tap-major copy for the row-major horizontal kernel
         for (uint32_t o = 0; o < nw; o++)
             for (uint32_t i = 0; i < ph; i++) wt[(size_t)i * nw + o] = st.h.ws[(size_t)o * ph + i];
@@ -273,9 +299,9 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
         st.uploaded = true;
     }
     const uint32_t *d_lv = st.d_tab + off_lv, *d_cv = st.d_tab + off_cv, *d_lh = st.d_tab + off_lh, *d_ch = st.d_tab + off_ch;
-    const float *d_wv = (const float *)(st.d_tab + off_wv), *d_wh = (const float *)(st.d_tab + off_wh),
-                *d_whr = (const float *)(st.d_tab + off_whr);
-    const uint32_t tpitch = (row_bytes + 3) / 4 * 4;
+    const float *d_wv = (const float *)(st.d_tab + off_wv), *d_nv = (const float *)(st.d_tab + off_nv),
+                *d_wh = (const float *)(st.d_tab + off_wh), *d_whr = (const float *)(st.d_tab + off_whr);
+    const uint32_t tpitch = (row_bytes + 7) / 8 * 8;
     // Transposed intermediate (see the header comment) for batches of photo -> tile reductions: both axes shrink 8x or more
     // (48+ taps amortise the four scattered stores of the vertical pass), at least a warp of output rows, and enough outputs
     // that the horizontal pass is throughput-bound.  Measured (tools/bench_resize.py, ncu launch lists under profiles/):
@@ -290,13 +316,13 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     if (per_pass > n) per_pass = n;
     if (per_pass > 32768) per_pass = 32768;
     if ((rc = emo_ensure(ctx, (void **)&st.tmp, &st.tmp_cap, tmp_per_img * per_pass))) return rc;
-    const bool aligned = ((uintptr_t)images % 4 == 0) && (img_bytes % 4 == 0) && (row_stride % 4 == 0) && (base_off % 4 == 0);
-    const uint32_t groups = tpitch / 4;
+    const bool aligned = ((uintptr_t)images % 8 == 0) && (img_bytes % 8 == 0) && (row_stride % 8 == 0) && (base_off % 8 == 0);
+    const uint32_t groups = tpitch / 8;
     for (uint32_t z0 = 0; z0 < n; z0 += per_pass) {
         const uint32_t nz = n - z0 < per_pass ? n - z0 : per_pass;
         const dim3 gv((groups + 255) / 256, nh, nz);
 #define EMO_VERTICAL(A, T)                                                                                                         \
-    resize_vertical_kernel<A, T><<<gv, 256, 0, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv, d_wv, pv, \
+    resize_vertical_kernel<A, T><<<gv, 256, 0, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv, d_wv, d_nv, pv, \
                                                              st.tmp, tpitch, nh, np, z0)
         if (transposed) {
             if (aligned) EMO_VERTICAL(true, true); else EMO_VERTICAL(false, true);
