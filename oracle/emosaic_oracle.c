@@ -11,15 +11,18 @@
  * restatement, function by function, of the reference sources cited below
  * (paths under /root/reference).  Arithmetic that lives in un-vendored crates
  * (kiddo 4.2.0 nearest_one/Manhattan, image 0.25.2 Rgba::blend / resize
- * Nearest / imageops::replace, bincode 1.3.3) is restated from the published
- * algorithms of those pinned versions.
+ * Nearest and Lanczos3 / imageops::replace, bincode 1.3.3) is restated from
+ * the published algorithms of those pinned versions.
  *
  * Parity pinning: every known-answer vector the reference's own unit tests
  * hold for this path (color.rs:49-72, analysis.rs:44-71, tile.rs:127-140,
  * utils.rs:302-308, mod.rs:83-161) is checked in tests/test_oracle_kat.py.
  * The argmin tie-break for > 320 tiles, the non-zero distance values, the
- * f32 tint blend and the cache byte layout have NO reference test or golden
- * vector: for those this oracle is "parity unpinned" (see DESIGN.md).
+ * f32 tint blend, the Lanczos3 resize (f32 two-pass sampler), the winner of
+ * most_common_value among equally frequent values and the cache byte layout
+ * have NO reference test or golden vector: for those this oracle is "parity
+ * unpinned" (see DESIGN.md).  The reference pins on this stage only
+ * utils.rs:284-289 (most_common_value) and :291-299 (prepare_tile is ts x ts).
  */
 #include <stdint.h>
 #include <stdlib.h>
