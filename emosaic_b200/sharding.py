@@ -2,7 +2,7 @@
 
 The match/compose path has no exchange step: block rows are independent, so rank r of `world`
 takes a contiguous range of block rows, holds the whole (replicated) library, and writes its own
-output slab; slabs are concatenated on the host.  The analysis build shards tiles the same way.
+output slab; slabs are concatenated on the host.  The analysis build and tile preparation shard tiles the same way.
 """
 from __future__ import annotations
 
@@ -31,7 +31,7 @@ def source_stripe(src, dim: int, world: int, rank: int):
 
 def gather_analysis(local, T: int, bytes_per_tile: int, world: int, rank: int, group=None):
     """Analysis cache build across GPUs (SURVEY §8e, C3): rank r analysed the tiles of `stripe_bounds(T, world, r)`;
-    all-gather the per-tile results (`bytes_per_tile` = 3*N) so every rank holds colours [T, bytes_per_tile].
+    all-gather the per-tile results (`bytes_per_tile` = 3*N for colours, 3*ts*ts for tiles prepared by emo_resize) so every rank holds [T, bytes_per_tile].
 
     `local` is a flat uint8 torch tensor (CUDA with the NCCL backend, CPU with gloo) of this rank's
     (stop - start) * bytes_per_tile bytes.  Ranges differ by at most one tile, so shards are padded to the

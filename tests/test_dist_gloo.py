@@ -112,3 +112,40 @@ def test_two_rank_analysis_build(T):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True and q.get(timeout=5) is True
+
+
+def _prepare_worker(rank, world, port, T, q):
+    sys.path.insert(0, ROOT)
+    import oracle
+    from emosaic_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ts = 8
+    photos = np.random.default_rng(78).integers(0, 230, (T, 40, 44, 3), dtype=np.uint8)   # same seed on every rank
+    a, b = sharding.stripe_bounds(T, world, rank)
+
+    def prep(p):  # the oracle stands in for emo_resize on this rank's photos (tiles/utils.rs:93-189)
+        return oracle.resize_lanczos3(p, ts, ts, oracle.prepare_view(p, ts, True))
+
+    local = np.stack([prep(p) for p in photos[a:b]]) if b > a else np.zeros((0, ts, ts, 3), np.uint8)
+    full = sharding.gather_analysis(torch.from_numpy(local.reshape(-1)), T, ts * ts * 3, world, rank)
+    want = np.stack([prep(p) for p in photos])
+    q.put(bool((full.numpy().reshape(T, ts, ts, 3) == want).all()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("T", [10, 7])
+def test_two_rank_tile_preparation(T):
+    """Tile preparation across ranks: each rank resizes its contiguous range of photos, the prepared tiles [T, ts, ts, 3] are
+    assembled by the same single all_gather as the analysis results (even and ragged split)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_prepare_worker, args=(r, 2, port, T, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True and q.get(timeout=5) is True
