@@ -44,14 +44,23 @@ int emo_create(int device, emo_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
-    EMO_CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    EMO_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    ctx->stream = ctx->own_stream;
-    EMO_CK(cudaEventCreate(&ctx->ev_start));
-    EMO_CK(cudaEventCreate(&ctx->ev_stop));
-    for (int i = 0; i < 4; i++) EMO_CK(cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
-    EMO_CK(cudaMalloc(&ctx->err_flag, sizeof(int)));
-    EMO_CK(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+    const int rc = [&]() -> int {
+        EMO_CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        EMO_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        EMO_CK(cudaEventCreate(&ctx->ev_start));
+        EMO_CK(cudaEventCreate(&ctx->ev_stop));
+        for (int i = 0; i < 4; i++) EMO_CK(cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
+        EMO_CK(cudaMalloc(&ctx->err_flag, sizeof(int)));
+        EMO_CK(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+        return EMO_OK;
+    }();
+    if (rc != EMO_OK) {  // a half-built ctx is released here; the error message of the failing call stays
+        const std::string msg = g_last_error;
+        emo_destroy(ctx);
+        g_last_error = msg;
+        return rc;
+    }
     *out = ctx;
     return EMO_OK;
 }

@@ -54,7 +54,8 @@ const char *emo_last_error(void);
 int emo_create(int device, emo_ctx **out);
 void emo_destroy(emo_ctx *ctx);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work; NULL
- * restores the ctx's own stream. */
+ * restores the ctx's own stream.  The ctx's scratch buffers are ordered on the stream in use:
+ * call emo_sync before switching streams while *_dev work is still in flight. */
 int emo_set_stream(emo_ctx *ctx, void *cuda_stream);
 int emo_sync(emo_ctx *ctx);
 /* Device name / SM count / compute capability of the ctx's GPU. */
