@@ -30,6 +30,10 @@
 //     every tap as one coalesced 128-byte row of the transposed image (the row-major layout costs 32 cache lines per load).
 //   resize_horizontal_kernel: one thread per (image, row, output pixel), lanes along the output row, weights stored
 //     tap-major ([tap][ox]) so that lanes read consecutive words.
+//   resize_horizontal_smem_kernel: row-major input whose output pixels are 4+ source pixels apart (a single photo, batches
+//     of very small tiles): the tmp row is staged into shared memory with coalesced loads (skewed by one word per 32 so
+//     that lanes 3*ratio floats apart hit different banks) and each thread runs its tap chain from there — the global
+//     version of this access pattern costs 32 cache lines per load.
 //   resize_horizontal_t_kernel: transposed input, one block per (image, output column), lanes along oy, weights uniform.
 //   resize_copy_kernel: the "(nwidth, nheight) == image.dimensions()" early return of resize() — a plain copy.
 #include <math.h>
@@ -198,6 +202,45 @@ resize_horizontal_kernel(const float *__restrict__ tmp, uint32_t tpitch, const u
     o[2] = clamp_round_u8(t2);
 }
 
+// Row-major intermediate, windows of neighbouring outputs far apart: stage the row in shared memory first.
+__device__ __forceinline__ uint32_t skew(uint32_t e) { return e + (e >> 5); }
+
+__global__ void __launch_bounds__(256)
+resize_horizontal_smem_kernel(const float *__restrict__ tmp, uint32_t tpitch, uint32_t row_floats, const uint32_t *__restrict__ left,
+                              const uint32_t *__restrict__ cnt, const float *__restrict__ wsT, uint32_t nw, uint32_t nh,
+                              uint8_t *__restrict__ out, uint32_t n0) {
+    extern __shared__ float srow[];
+    const uint32_t y = blockIdx.x, n = blockIdx.y + n0;
+    const float *__restrict__ row = tmp + ((size_t)blockIdx.y * nh + y) * tpitch;
+    for (uint32_t e = threadIdx.x * 4; e < row_floats; e += blockDim.x * 4) {  // tpitch is a multiple of 8: whole float4s exist
+        const float4 v = __ldg((const float4 *)(row + e));
+        const uint32_t s = skew(e);  // e % 4 == 0: the four words share one skew
+        srow[s] = v.x;
+        srow[s + 1] = v.y;
+        srow[s + 2] = v.z;
+        srow[s + 3] = v.w;
+    }
+    __syncthreads();
+    for (uint32_t ox = threadIdx.x; ox < nw; ox += blockDim.x) {
+        const uint32_t c = cnt[ox];
+        const uint32_t base = left[ox] * 3;
+        const float *__restrict__ w = wsT + ox;
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+#pragma unroll 4
+        for (uint32_t i = 0; i < c; i++) {
+            const float wi = __ldg(w + (size_t)i * nw);
+            const uint32_t e = base + 3 * i;
+            t0 = __fadd_rn(t0, __fmul_rn(srow[skew(e)], wi));
+            t1 = __fadd_rn(t1, __fmul_rn(srow[skew(e + 1)], wi));
+            t2 = __fadd_rn(t2, __fmul_rn(srow[skew(e + 2)], wi));
+        }
+        uint8_t *o = out + (((size_t)n * nh + y) * nw + ox) * 3;
+        o[0] = clamp_round_u8(t0);
+        o[1] = clamp_round_u8(t1);
+        o[2] = clamp_round_u8(t2);
+    }
+}
+
 // Transposed intermediate [x*3+c][oy] (np floats per line): one block per (image, output column), lanes along oy, so a
 // tap is three coalesced loads and the weight is uniform across the block.
 __global__ void __launch_bounds__(128)
@@ -306,7 +349,8 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     // (48+ taps amortise the four scattered stores of the vertical pass), at least a warp of output rows, and enough outputs
     // that the horizontal pass is throughput-bound.  Measured (tools/bench_resize.py, ncu launch lists under profiles/):
     // 64 x 2048^2 -> 64^2 horizontal pass 615 -> 90 us; but 8192^2 -> 4096^2 (13 taps) 2.7x slower and a single
-    // 4000x3000 photo (4096 outputs, latency-bound, the row-major layout keeps a thread's taps in one L1 line) 1.3x slower.
+    // 4000x3000 photo (4096 outputs, latency-bound, the row-major layout keeps a thread's taps in one L1 line) 1.3x slower;
+    // such geometries take the shared-memory staged horizontal pass below instead.
     const bool transposed = cw >= 8 * (uint64_t)nw && ch >= 8 * (uint64_t)nh && nh >= 32 && (uint64_t)n * nh * nw >= 65536;
     const uint32_t np = (nh + 31) / 32 * 32;
     // images per pass: bounded by the f32 intermediate (<= 1 GiB) and the grid's z extent
@@ -318,6 +362,11 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     if ((rc = emo_ensure(ctx, (void **)&st.tmp, &st.tmp_cap, tmp_per_img * per_pass))) return rc;
     const bool aligned = ((uintptr_t)images % 8 == 0) && (img_bytes % 8 == 0) && (row_stride % 8 == 0) && (base_off % 8 == 0);
     const uint32_t groups = tpitch / 8;
+    // row-major intermediate with outputs 4+ source pixels apart: stage each row in shared memory (skewed), if it fits
+    const size_t smem_row = ((size_t)tpitch + tpitch / 32 + 8) * 4;
+    const bool staged = !transposed && cw >= 4 * (uint64_t)nw && smem_row <= 200 * 1024;
+    if (staged && smem_row > 48 * 1024)
+        EMO_CK(cudaFuncSetAttribute(resize_horizontal_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     for (uint32_t z0 = 0; z0 < n; z0 += per_pass) {
         const uint32_t nz = n - z0 < per_pass ? n - z0 : per_pass;
         const dim3 gv((groups + 255) / 256, nh, nz);
@@ -335,6 +384,10 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
             const uint32_t bt = nh >= 128 ? 128 : (nh + 31) / 32 * 32;
             resize_horizontal_t_kernel<<<dim3(nw, (nh + bt - 1) / bt, nz), bt, 0, ctx->stream>>>(st.tmp, tpitch, np, d_lh, d_ch, d_whr, ph,
                                                                                                nw, nh, out, z0);
+        } else if (staged) {
+            const uint32_t bt = nw >= 256 ? 256 : (nw + 31) / 32 * 32;
+            resize_horizontal_smem_kernel<<<dim3(nh, nz), bt, smem_row, ctx->stream>>>(st.tmp, tpitch, row_bytes, d_lh, d_ch, d_wh, nw,
+                                                                                      nh, out, z0);
         } else {
             resize_horizontal_kernel<<<dim3((nw + 127) / 128, nh, nz), 128, 0, ctx->stream>>>(st.tmp, tpitch, d_lh, d_ch, d_wh, nw, nh,
                                                                                             out, z0);
