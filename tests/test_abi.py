@@ -59,3 +59,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 on its own (what a Rust bindgen / cgo would parse)."""
+    import shutil
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not cc:
+        pytest.skip("no C compiler")
+    r = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "emosaic_cuda.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_resize_null_and_argument_checks_need_no_gpu():
+    """Argument validation of emo_resize happens before any CUDA call (NULL ctx is rejected first)."""
+    from emosaic_b200 import _lib
+    lib = _lib.load()
+    assert lib.emo_resize(None, None, 1, 4, 4, 0, 0, 4, 4, 2, 2, None) == -1
+    assert b"ctx is NULL" in lib.emo_last_error()
