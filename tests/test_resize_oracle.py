@@ -133,3 +133,37 @@ def test_rotate_orientations():
 def test_source_dimension_rule_matches_oracle():
     for w, h, ds, dim in [(101, 103, 1, 2), (1023, 77, 2, 3), (4096, 4096, 1, 1), (50, 50, 7, 4), (5, 5, 1, 4)]:
         assert api.adjust_source_dims(w, h, ds, dim) == oracle.adjust_dims(w, h, ds, dim)
+
+
+def test_oracle_tracks_exact_lanczos3():
+    """The f32 two-pass restatement against the same filter evaluated in float64 with exact normalisation: the results may
+    differ only where f32 rounding moves a value across a .5 boundary, i.e. by at most one level (checks the algorithm —
+    window, weights, normalisation, clamp, rounding mode — independently of the f32 operation order)."""
+    rng = np.random.default_rng(42)
+
+    def exact_axis(n_in, n_out):
+        ratio = n_in / n_out
+        sratio = max(ratio, 1.0)
+        taps = []
+        for o in range(n_out):
+            c = (o + 0.5) * ratio
+            left = min(max(int(np.floor(c - 3 * sratio)), 0), n_in - 1)
+            right = min(max(int(np.ceil(c + 3 * sratio)), left + 1), n_in)
+            x = (np.arange(left, right) - (c - 0.5)) / sratio
+            w = np.where(np.abs(x) < 3, np.sinc(x) * np.sinc(x / 3), 0.0)
+            taps.append((left, w / w.sum()))
+        return taps
+
+    worst = 0
+    for h, w, nh, nw in [(40, 52, 12, 12), (33, 29, 47, 61), (64, 64, 63, 62), (90, 70, 9, 7)]:
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.clip(np.stack([np.sin(xx / 5.0) * 120 + 128, np.cos(yy / 4.0) * 120 + 128, (xx * 7 + yy * 3) % 256], -1)
+                      + rng.integers(-10, 11, (h, w, 3)), 0, 255).astype(np.uint8)
+        tmp = np.stack([sum(img[l + i].astype(np.float64) * wt for i, wt in enumerate(ws)) for l, ws in exact_axis(h, nh)])
+        ex = np.stack([sum(tmp[:, l + i] * wt for i, wt in enumerate(ws)) for l, ws in exact_axis(w, nw)], axis=1)
+        ex = np.floor(np.clip(ex, 0, 255) + 0.5)
+        got = oracle.resize_lanczos3(img, nw, nh).astype(np.float64)
+        diff = np.abs(got - ex)
+        worst = max(worst, int(diff.max()))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.02
+    assert worst <= 1
