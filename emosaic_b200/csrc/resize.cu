@@ -8,8 +8,9 @@
 //   horizontal_sample: out[y][ox][c] = round(clamp(sum_i tmp[y][left(ox) + i][c] * w(ox, i), 0, 255))
 // with every tap one f32 multiply followed by one f32 add (Rust never contracts to FMA), taps in ascending order.
 // f32 addition is not associative, so a tap loop is inherently sequential per output element and both kernels keep
-// that order; the parallelism is across output elements.  The multiply and the add are issued with __fmul_rn /
-// __fadd_rn so ptxas cannot fuse them.
+// that order; the parallelism is across output elements.  Every rounding of the reference is kept: the horizontal pass
+// issues the multiply and the add as __fmul_rn / __fadd_rn so ptxas cannot fuse them, the vertical pass forms the
+// once-rounded product with an FMA (below) and adds separately.
 //
 // The tap tables (left, count, normalised Lanczos3 weights: O(nw + nh) numbers, each needing the platform's libm sinf
 // exactly as f32::sin does in the reference) are computed on the host in resize_axis() and cached per geometry; all
@@ -22,8 +23,9 @@
 //     RN((2^23 + b) * w - 2^23 * w) = RN(b * w), because the FMA adds the exact 48-bit product to the exactly representable
 //     -2^23 * w and rounds once — the same single rounding as the reference's multiply.  The add that accumulates stays
 //     a separate FADD: 3 instructions per byte and tap (PRMT, FFMA, FADD) instead of 4.  w and -2^23 * w come from the
-//     table as one 128-bit load per four taps each.  The kernel is issue-bound (ncu: 86 % of the issue slots, DRAM 14 %,
-//     L2 30 %): the ~6x re-read of a source row by neighbouring output rows is served by L1/L2 and is not the limiter.
+//     table as one 128-bit load per four taps each.  The kernel is issue-bound (ncu, 64 x 2048^2 -> 64^2: 70 % of the issue
+//     slots, ALU pipe 53 %, DRAM 14 %, L2 32 %; DRAM reads = the algorithmic bytes): the ~6x re-read of a source row by
+//     neighbouring output rows is served by L1/L2 and is not the limiter.
 //   tmp layout: row-major [oy][x*3+c] (pitch padded to 8 floats, two float4 stores per thread) when the image is about as
 //     wide as the output (source resize); TRANSPOSED [x*3+c][oy] for batches whose axes both shrink 8x or more (photo -> tile): there
 //     the windows of neighbouring output pixels lie far apart, so the horizontal pass runs with lanes along oy and reads
