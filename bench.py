@@ -419,6 +419,14 @@ def run_ours(args):
         }
         if world == 1 and not args.no_extras:
             extra.update(extras(ctx, torch, dev, hbm_peak, peak_src))
+            c2 = extra.get("c2_4to1", {})
+            if "match_ms" in c2 and sad > 0:  # C2 (BASELINE configs[1]): the 4to1 scan against the VABSDIFF4 rate measured in this run
+                pairs2 = (1024 // 2) ** 2 * 20000
+                c2["roofline"] = {"kernel": "match_kernel<3,2,128>", "bound": "int32-pipe (VABSDIFF4)", "unit": "T abs-diff-words/s",
+                                  "achieved": 3 * pairs2 / (c2["match_ms"] * 1e-3) / 1e12, "peak": sad / 1e12,
+                                  "frac": 3 * pairs2 / (c2["match_ms"] * 1e-3) / sad, "traffic": None,
+                                  "note": "3 VABSDIFF4 per (block, candidate) pair (12 bytes); the inner loop's IMAD / VIMNMX3 share "
+                                          "caps the fraction at 0.92"}
         if c3_sharded is not None:
             extra["c3_analysis_sharded"] = c3_sharded
         if weak is not None:
