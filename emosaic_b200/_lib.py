@@ -18,7 +18,7 @@ EXPORTS = [
     "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_build_index",
     "emo_set_match_mode", "emo_match", "emo_topk", "emo_topk_dev",
     "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev",
-    "emo_probe_int_pipe", "emo_resize", "emo_resize_dev",
+    "emo_probe_int_pipe", "emo_resize", "emo_resize_dev", "emo_resize_taps",
 ]
 
 _lib = None
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
         "emo_probe_int_pipe": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
         "emo_resize": (C.c_int, [vp, u8p] + [C.c_uint32] * 9 + [u8p]),
         "emo_resize_dev": (C.c_int, [vp, u8p] + [C.c_uint32] * 9 + [u8p]),
+        "emo_resize_taps": (C.c_int, [C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the export is missing

@@ -451,6 +451,18 @@ def adjust_source_dims(w: int, h: int, downsample: int, dim: int):
     return nw, nh
 
 
+def resize_taps(n_in: int, n_out: int):
+    """The tap table of one axis as emo_resize computes it (host-only): (left [n_out], cnt [n_out], weights [n_out, max taps])."""
+    lib = _lib.load()
+    mt = C.c_uint32(0)
+    check(lib.emo_resize_taps(n_in, n_out, None, None, None, 0, C.byref(mt)))
+    left = np.zeros(n_out, np.uint32)
+    cnt = np.zeros(n_out, np.uint32)
+    ws = np.zeros((n_out, mt.value), np.float32)
+    check(lib.emo_resize_taps(n_in, n_out, _ptr(left), _ptr(cnt), _ptr(ws), mt.value, None))
+    return left, cnt, ws
+
+
 def resize_source(original_img, downsample: int, dim: int, ctx: Context | None = None) -> np.ndarray:
     """main.rs:567-595: the copy of the source that is matched — ``imageops::resize(original, nw, nh, Lanczos3)`` with
     (nw, nh) from the dimension rule; equal dimensions give a plain copy, as in the crate."""

@@ -96,6 +96,25 @@ static void resize_axis(uint32_t n_in, uint32_t n_out, emo_resize_axis &ax) {
     }
 }
 
+// Diagnostic export: the tap table of one axis exactly as emo_resize computes it (host-only, no ctx, no GPU).
+extern "C" int emo_resize_taps(uint32_t n_in, uint32_t n_out, uint32_t *left, uint32_t *cnt, float *ws, uint32_t pitch,
+                               uint32_t *max_taps) {
+    EMO_REQUIRE(n_in >= 1 && n_out >= 1, EMO_ERR_ARG, "resize_taps: empty axis (%u -> %u)", n_in, n_out);
+    emo_resize_axis ax;
+    resize_axis(n_in, n_out, ax);
+    if (max_taps) *max_taps = ax.pitch;
+    if (left) memcpy(left, ax.left.data(), (size_t)n_out * 4);
+    if (cnt) memcpy(cnt, ax.cnt.data(), (size_t)n_out * 4);
+    if (ws) {
+        EMO_REQUIRE(pitch >= ax.pitch, EMO_ERR_ARG, "resize_taps: pitch %u below the largest tap count %u", pitch, ax.pitch);
+        for (uint32_t o = 0; o < n_out; o++) {
+            memset(ws + (size_t)o * pitch, 0, (size_t)pitch * 4);
+            memcpy(ws + (size_t)o * pitch, ax.ws.data() + (size_t)o * ax.pitch, (size_t)ax.cnt[o] * 4);
+        }
+    }
+    return EMO_OK;
+}
+
 // ---- device ---------------------------------------------------------------------------------------------------------------
 // RN(f32(byte K of v) * w) in one FFMA: x = 2^23 + b (PRMT), nbw = -2^23 * w (exact), fma(x, w, nbw) rounds b * w once
 template <int K>

@@ -95,6 +95,14 @@ int emo_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t img_w, 
 int emo_resize_dev(emo_ctx *ctx, const uint8_t *images_dev, uint32_t n, uint32_t img_w, uint32_t img_h, uint32_t x0,
                    uint32_t y0, uint32_t cw, uint32_t ch, uint32_t nw, uint32_t nh, uint8_t *out_dev);
 
+/* The tap table of one axis exactly as emo_resize computes it: for every output index the first source index
+ * (left[n_out]), the tap count (cnt[n_out]) and the normalised Lanczos3 weights (ws[n_out][pitch], zero beyond
+ * cnt).  Host-only (no ctx, no GPU): for inspection and for checking the host side of the library against
+ * another implementation of image 0.25.2's sampler set-up.  Any output pointer may be NULL; *max_taps receives
+ * the largest tap count (the minimum pitch). */
+int emo_resize_taps(uint32_t n_in, uint32_t n_out, uint32_t *left, uint32_t *cnt, float *ws, uint32_t pitch,
+                    uint32_t *max_taps);
+
 /* ---- (1) tile analysis ------------------------------------------------------------------
  * Replaces analyse::<N>() (src/mosaic/analysis.rs:5-20) + average_color()
  * (src/mosaic/color.rs:14-42) looped over the library (src/main.rs:786-794).

@@ -167,3 +167,14 @@ def test_oracle_tracks_exact_lanczos3():
         worst = max(worst, int(diff.max()))
         assert diff.max() <= 1 and (diff > 0).mean() < 0.02
     assert worst <= 1
+
+
+@pytest.mark.parametrize("n_in,n_out", [(4097, 4096), (4098, 4096), (8192, 4096), (3000, 64), (2048, 64), (256, 8), (37, 36), (45, 44), (7, 31),
+                                        (1, 5), (300, 1), (1024, 4096), (64, 64), (100, 99), (1000, 333)])
+def test_library_tap_tables_equal_the_oracle(n_in, n_out):
+    """The host side of libemosaic_cuda.so (resize_axis in resize.cu, exported as emo_resize_taps; no GPU involved) against the
+    oracle's restatement of sample.rs: same windows, bit-identical f32 weights."""
+    left, cnt, ws = api.resize_taps(n_in, n_out)
+    ol, oc, ow = oracle.resize_axis(n_in, n_out)
+    assert (left == ol).all() and (cnt == oc).all() and ws.shape == ow.shape
+    assert (ws.view(np.uint32) == ow.view(np.uint32)).all()
