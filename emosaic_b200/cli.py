@@ -118,8 +118,7 @@ def main(argv=None) -> int:
             return 1
         return 0
     if args.subcmd != "mosaic":
-        print("error: a subcommand is required (mosaic | prepare)", file=sys.stderr)
-        return 2
+        return 0  # main.rs:378-379 `None => ()`: without a subcommand the reference validates its arguments and does nothing
     if not (0.0 <= args.tint_opacity <= 1.0):
         print("error: Value must be between 0 and 1", file=sys.stderr)
         return 2

@@ -1,6 +1,7 @@
 // cli.cpp — `emosaic` with the reference's command line (src/main.rs:28-138) for the accelerated path, C++ host.
 //   emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m 1|2|...|128|1to1|4to1|random] [-f] [-t X] [--downsample K]
 //           [--extensions e ...]
+//   emosaic [-s N] [-o PATH] [--crop] IMG prepare          (main.rs:380-386: one prepared tile)
 // Tiles and the source are decoded by the minimal PNG/PPM reader of emosaic.cpp (no libjpeg in this image; the Python
 // front end `python -m emosaic_b200` decodes JPEG with PIL).  A tile that is already tile_size x tile_size is taken as
 // prepared (the role of the reference's ~/.cache/mosaic hit, utils.rs:73-85); any other tile goes through prepare_tile
@@ -42,7 +43,7 @@ static void find_images(const std::string &dir, const std::vector<std::string> &
 int main(int argc, char **argv) {
     uint32_t tile_size = 16;
     std::string output = "./output.jpg", img_path, tiles_dir, mode = "1";
-    bool crop = false, force = false, mosaic = false, no_repeat = false;
+    bool crop = false, force = false, mosaic = false, prepare = false, no_repeat = false;
     double tint = 0.0;
     uint32_t downsample = 1;
     std::vector<std::string> exts = {"jpg", "jpeg"}, pos;
@@ -62,10 +63,21 @@ int main(int argc, char **argv) {
             fprintf(stderr, "error: %s is outside the accelerated path\n", a.c_str());
             return 2;
         } else if (a == "mosaic") mosaic = true;
+        else if (a == "prepare") prepare = true;
         else pos.push_back(a);
     }
+    if (prepare && !mosaic && pos.size() == 1) {  // main.rs:380-386: prepare_tile(&img, tile_size, crop) saved to the output path
+        try {
+            Context ctx(0);
+            write_png(output, prepare_tile(ctx, read_image(pos[0]), tile_size, crop));
+        } catch (const Error &e) {
+            fprintf(stderr, "error: Failed to prepare tile from %s: %s\n", pos[0].c_str(), e.what());
+            return 1;
+        }
+        return 0;
+    }
     if (!mosaic || pos.size() != 2) {
-        fprintf(stderr, "usage: emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m MODE] [-f] [-t X]\n");
+        fprintf(stderr, "usage: emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m MODE] [-f] [-t X] | IMG prepare\n");
         return 2;
     }
     if (!(tint >= 0.0 && tint <= 1.0)) { fprintf(stderr, "error: Value must be between 0 and 1\n"); return 2; }

@@ -32,7 +32,7 @@ def test_python_cli_validation(work):
     (d / "notes.txt").write_text("x")
     assert cli.main(["-s", "8", str(d / "notes.txt"), "mosaic", tiles]) == 1     # unsupported format
     assert cli.main(["-s", "8", "-o", str(d / "nodir" / "o.png"), src, "mosaic", tiles]) == 1   # validate_output_path
-    assert cli.main(["-s", "8", src]) == 2                                        # a subcommand is required
+    assert cli.main(["-s", "8", src]) == 0                                        # main.rs:378-379 `None => ()`: validated, nothing to do
     assert cli.main(["-s", "8", src, "mosaic", tiles, "-t", "1.5"]) == 2          # "Value must be between 0 and 1"
     assert cli.main(["-s", "8", src, "mosaic", tiles, "--no-repeat", "--greedy"]) == 2
     assert cli.main(["-s", "8", src, "mosaic", tiles, "--randomize", "5"]) == 2
@@ -82,3 +82,5 @@ def test_cpp_cli_validation_and_no_gpu(work):
     if not torch.cuda.is_available():
         r = run("-s", "8", "-o", str(d / "o.png"), src, "mosaic", tiles, "--extensions", "png")
         assert r.returncode == 1 and "no CPU path" in r.stderr
+        r = run("-s", "8", "-o", str(d / "t.png"), src, "prepare")                  # main.rs:380-386
+        assert r.returncode == 1 and "Failed to prepare tile" in r.stderr and "no CPU path" in r.stderr

@@ -142,3 +142,13 @@ def test_cli_no_repeat(workdir):
     item, dist = onp.no_repeat_assign(colors, small)
     assert (np.asarray(PIL.open(out)) == oracle.render(px_rd, item)).all()
     assert len(set(np.abs(item).reshape(-1).tolist())) == item.size
+
+
+def test_cli_prepare_subcommand(workdir):
+    """`emosaic -s N [--crop] IMG prepare` (main.rs:380-386): one prepared tile, saved to the output path."""
+    d, _ = workdir
+    photo = cli.find_images(str(d / "tiles"), {"jpg", "jpeg"})[0]   # t000: has a white frame
+    for crop in (False, True):
+        out = d / f"prepared_{int(crop)}.png"
+        assert cli.main(["-s", "12", "-o", str(out)] + (["--crop"] if crop else []) + [photo, "prepare"]) == 0
+        assert (np.asarray(PIL.open(out)) == oracle_tile(photo, 12, crop)).all()

@@ -146,3 +146,22 @@ def test_cpp_cli_prepares_tiles_and_resizes_source(tmp_path):
         r = subprocess.run(args + ["-t", "0.5"], capture_output=True, text=True, timeout=120)   # cache reuse + tint
         assert r.returncode == 0 and "Reusing analysis cache" in r.stderr, r.stderr
         assert (np.asarray(PIL.open(out)) == oracle.tint(oracle.render(px_rd, item), src, 127)).all()
+
+
+@pytest.mark.gpu
+def test_cpp_cli_prepare_subcommand(tmp_path):
+    """`emosaic -s N [--crop] IMG prepare` (main.rs:380-386) in the C++ front end."""
+    import oracle
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(8)
+    img = np.full((50, 64, 3), 255, np.uint8)
+    img[4:45, 6:60] = rng.integers(0, 220, (41, 54, 3))
+    PIL.fromarray(img).save(tmp_path / "photo.png")
+    exe = _need("emosaic")
+    for crop in (False, True):
+        out = tmp_path / f"tile{int(crop)}.png"
+        r = subprocess.run([exe, "-s", "16", "-o", str(out)] + (["--crop"] if crop else []) + [str(tmp_path / "photo.png"), "prepare"],
+                           capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        want = oracle.resize_lanczos3(img, 16, 16, oracle.prepare_view(img, 16, crop))
+        assert (np.asarray(PIL.open(out)) == want).all()
