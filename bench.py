@@ -6,7 +6,8 @@
 
 Workload (config.workload): C4 = `--mode 1 -s 8`, 100 000 synthetic 8x8 tiles, 4096x4096 synthetic source
 -> 32768x32768x3 output, source block rows sharded over the N ranks (strong scaling, no collective in the
-loop; the library + source are replicated once with an NCCL broadcast).  A step = one pass (match every
+loop; the library + source are replicated once by the product's own NCCL broadcast, emo_comm_set_library_dev /
+emo_comm_broadcast_dev of libemosaic_cuda.so — torch.distributed only provides the barrier and the max-over-ranks reduction).  A step = one pass (match every
 source pixel against the whole library, then composite the output stripe).  The library side is prepared once
 per rank before the loop, like the replicated library of the north star: analysis, the (tile, mirror) pixel
 store and the 1to1 search index (the GPU stand-in for build_kiddo, tileset.rs:178-190; its build time is
@@ -43,6 +44,19 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(kernel: str, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on this workload at N = 1, from
+    profiles/traffic.json — written by `tools/summarise_ncu.py traffic` from an `ncu --set full` capture together with the
+    commit it was taken at.  None when there is no capture (or at N > 1, where the stripe is a different launch)."""
+    if world != 1:
+        return None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(kernel)
+        return int(rec["dram_bytes"]) if rec else None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class ClockSampler:
@@ -198,8 +212,6 @@ def run_ours(args):
     import torch.distributed as dist
 
     import emosaic_b200 as emo
-    from emosaic_b200 import sharding
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,25 +239,30 @@ def run_ours(args):
     T, ts, W, H, N = cfg["T"], cfg["ts"], cfg["W"], cfg["H"], cfg["N"]
     ctx = emo.Context(local_rank)
     info = ctx.device_info()
+    comm = None
+    if world > 1:   # the product's own communicator: the 128-byte NCCL id travels through torchrun's store
+        box = [emo.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init_rank(box[0], rank, world)
+        comm = ctx.comm_info()
 
-    # ---- inputs: rank 0 synthesises, one NCCL broadcast replicates library + source ----------------
-    tiles_d = torch.empty(T * ts * ts * 3, dtype=torch.uint8, device=dev)
+    # ---- inputs: rank 0 synthesises and analyses; libemosaic_cuda.so replicates library + source over NCCL ----
     src_d = torch.empty(H * W * 3, dtype=torch.uint8, device=dev)
-    src_h = None
     if rank == 0:
         tiles_h, src_h = synth_c4(cfg)
-        tiles_d.copy_(torch.from_numpy(tiles_h).reshape(-1))
+        tiles_d = torch.from_numpy(tiles_h).reshape(-1).to(dev)
         src_d.copy_(torch.from_numpy(src_h).reshape(-1))
-    if world > 1:
-        dist.broadcast(tiles_d, 0)
-        dist.broadcast(src_d, 0)
-    torch.cuda.synchronize()
-    colors_d = torch.empty(T * N * 3, dtype=torch.uint8, device=dev)
-    ctx.analyse_dev(tiles_d.data_ptr(), T, ts, 1, colors_d.data_ptr())   # library analysis on the GPU
-    ctx.set_library_dev(colors_d.data_ptr(), tiles_d.data_ptr(), T, N, ts)
+        colors_d = torch.empty(T * N * 3, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctx.analyse_dev(tiles_d.data_ptr(), T, ts, 1, colors_d.data_ptr())   # library analysis on the GPU
+        ctx.comm_set_library_dev(colors_d.data_ptr(), tiles_d.data_ptr(), T, N, ts, root=0)
+    else:
+        ctx.comm_set_library_dev(0, 0, 0, 0, 0, root=0)
+    ctx.comm_broadcast_dev(src_d.data_ptr(), H * W * 3, root=0)
     ctx.sync()
+    assert (ctx.T, ctx.N, ctx.ts) == (T, N, ts), "library did not arrive"
 
-    a, b = sharding.stripe_bounds(H, world, rank)      # dim == 1: block rows == source rows
+    a, b = emo.stripe_bounds(H, world, rank)           # emo_stripe_bounds; dim == 1: block rows == source rows
     Hs = b - a
     src_ptr = src_d.data_ptr() + a * W * 3
     item_d = torch.empty(Hs * W, dtype=torch.int32, device=dev)
@@ -336,6 +353,26 @@ def run_ours(args):
     ctx.host_free(src_pin)
     ctx.host_free(out_pin)
 
+    # ---- what the host side can absorb: every rank drains a buffer of its stripe's size to pinned memory at the same
+    # time (one cudaMemcpyAsync per 64 MB piece, like emo_mosaic), and rank 0 once alone.  e2e is bound by these figures.
+    host = None
+    if not args.no_extras:
+        from tools import probe
+        stripe_out = Hs * ts * W * ts * 3
+        barrier()
+        _, per = probe.host_copy([local_rank], stripe_out, 64 << 20, "d2h", 3)
+        barrier()
+        t_all = max_over_ranks(stripe_out * 3 / (per[0] * 1e9))            # slowest rank's time for its 3 passes
+        solo = None
+        if rank == 0:
+            _, per0 = probe.host_copy([local_rank], stripe_out, 64 << 20, "d2h", 3)
+            solo = per0[0]
+        barrier()
+        host = {"d2h_all_ranks_gbs": H * ts * W * ts * 3 * 3 / t_all / 1e9, "d2h_one_rank_alone_gbs": solo,
+                "bytes_per_rank": stripe_out, "piece": 64 << 20,
+                "note": "pinned cudaHostAlloc buffers, every rank copying its stripe-sized buffer device->host at once "
+                        "(tools/probe/hostcopy.cu); aggregate = whole-image bytes / slowest rank's time"}
+
     # ---- context for the strong-scaling number: the same step with a whole 4096 x 4096 source per rank (weak scaling) ----
     weak = None
     if world > 1 and not args.no_extras:
@@ -363,7 +400,33 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     hbm_peak, peak_src = peaks()
-    c3_sharded = c3_across_ranks(ctx, torch, dist, dev, world, rank, max_over_ranks, barrier) if world > 1 and not args.no_extras else None
+    c3_sharded = c3_across_ranks(ctx, emo, torch, dev, world, rank, max_over_ranks, barrier) if world > 1 and not args.no_extras else None
+
+    # ---- one process driving all N GPUs (emo_group_mosaic: stripes copied straight into ONE pinned host image) next to
+    # the N-process e2e above; rank 0 runs it while the other ranks wait at the barrier.
+    group_e2e = None
+    if world > 1 and not args.no_extras:
+        barrier()
+        if rank == 0:
+            try:
+                group_e2e = group_e2e_record(emo, ctx, world, cfg, tiles_h, colors_d.cpu().numpy().reshape(T, N, 3), src_h)
+            except Exception as e:  # noqa: BLE001
+                group_e2e = {"error": str(e)}
+        barrier()
+
+    # ---- pipe rates measured in this run (tools/libemosaic_probe.so; rank 0) ---------------------
+    probes = None
+    if rank == 0:
+        from tools import probe
+        probes = {"imad": probe.probe_int_pipe(local_rank, 0), "vabsdiff4": probe.probe_int_pipe(local_rank, 1),
+                  "vimnmx3": probe.probe_int_pipe(local_rank, 2)}
+    # ---- C2 (BASELINE configs[1], 4to1): first-class record at every N, row-sharded like the headline ----
+    c2 = None
+    if not args.no_extras:
+        try:
+            c2 = c2_record(ctx, emo, torch, dev, world, rank, args, max_over_ranks, barrier, probes["vabsdiff4"] if probes else 0.0)
+        except Exception as e:  # noqa: BLE001
+            c2 = {"error": str(e)}
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel of the step: compose_tile_kernel<8> (HBM writes) -----------
@@ -373,80 +436,79 @@ def run_ours(args):
             "kernel": "compose_tile_kernel<8>", "bound": "hbm",
             "achieved": comp_bytes / (comp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": comp_bytes / (comp_ms * 1e-3) / 1e9 / hbm_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload at N=1, from the committed
-            # ncu --set full capture profiles/r01g_ncu_full_compose_tile_kernel.txt (78.3 MB + 3162.6 MB)
-            "traffic": 3240965504 if world == 1 else None,
+            "traffic": measured_traffic("compose_tile_kernel", world),
             "peak_source": peak_src, "ms_per_launch": comp_ms, "share_of_step": comp_ms / (comp_ms + match_ms),
             "note": "achieved = (output stripe + item map + tile library once) bytes / CUDA-event time of the compose "
                     "launch (avg over the timed steps, rank 0); the peak is the measured read+write copy figure, which a "
-                    "write-mostly stream can exceed by a few per cent",
+                    "write-mostly stream can exceed by a few per cent; traffic = dram bytes of one launch from the ncu capture "
+                    "recorded in profiles/traffic.json (null when no capture of this build exists)",
         }
         # the index lookup: 3 B of source in, 8 B of item/dist out per block, plus one gather from the L2-resident table
         look_bytes = Hs * W * 11
-        imad = ctx.probe_int_pipe(0)
-        sad = ctx.probe_int_pipe(1)
-        mnmx = ctx.probe_int_pipe(2)
-        mix = ctx.probe_int_pipe(3)
+        sad = probes["vabsdiff4"]
         D = 3 * N
         L = T if N == 1 else 2 * T
         pairs_per_launch = (Hs * W) * L
-        ops = 2 * D * pairs_per_launch                      # 2*D integer ops per (query, candidate) pair
-        achieved = ops / (scan_ms * 1e-3)
+        pairs_per_s = pairs_per_launch / (scan_ms * 1e-3)
+        step_ms = ms / args.steps
         extra = {
             "match_ms": match_ms_max, "compose_ms": comp_ms_max, "index_build_ms": index_build_ms,
-            # the per-library work is outside the step on both arms (KD-tree build on the CPU arm, index build here);
-            # for reference, the figure if every step rebuilt the index as rendering.rs:136 rebuilds the tree per render
-            "value_if_index_rebuilt_every_step": Q_total / ((ms / args.steps + index_build_ms) * 1e-3),
+            # rendering.rs:136 builds the KD-tree inside render_nto1, i.e. once per render: the per-render figure pays the
+            # index build (the GPU stand-in for that tree) in every step
+            "value_per_render": Q_total / ((step_ms + index_build_ms) * 1e-3),
             "composed_output_gbs": (H * ts * W * ts * 3) / (comp_ms_max * 1e-3) / 1e9,
             "roofline_match_index": {"kernel": "match_index_kernel", "bound": "hbm", "achieved": look_bytes / (match_ms * 1e-3) / 1e9,
                                      "peak": hbm_peak, "unit": "GB/s", "frac": look_bytes / (match_ms * 1e-3) / 1e9 / hbm_peak,
-                                     "traffic": None, "ms_per_launch": match_ms,
-                                     "note": "algorithmic bytes = 11 B per block; the 64 MiB table is gathered from L2"},
+                                     "traffic": measured_traffic("match_index_kernel", world), "ms_per_launch": match_ms,
+                                     "note": "algorithmic bytes = 11 B per block (3 B of source in, 8 B of item + dist out)"},
             "match_scan": {
-                "kernel": "match_kernel<1,8,256>", "bound": "int32-pipe", "ms_per_launch": scan_ms_max, "steps": scan_steps,
+                "kernel": "match_kernel<1,8,256>", "bound": "int32-pipe (VABSDIFF4)", "ms_per_launch": scan_ms_max, "steps": scan_steps,
                 "matched_px_per_s": Q_total / ((scan_ms_max + comp_ms_max) * 1e-3),
-                "achieved": achieved / 1e12, "peak": imad / 1e12, "unit": "Tint-op/s", "frac": achieved / imad,
-                # profiles/r01e_ncu_full_match_kernel.txt (55.1 MB + 81.2 MB)
-                "traffic": 136288512 if world == 1 else None,
-                "note": "the same step with EMO_MATCH_SCAN: achieved = 2*D*Q*L algorithmic integer ops / CUDA-event time of "
-                        "the scan launch; peak = scalar INT32 (IMAD) issue rate measured by emo_probe_int_pipe in this run; "
-                        "frac > 1 is legitimate because one VABSDIFF4.U8.ACC performs 4 abs-diffs + 3 adds",
-                "pairs_per_s": pairs_per_launch / (scan_ms * 1e-3),
-                "mix_peak_pairs_per_s": mix / 1.5,
-                "frac_of_mix_peak": (pairs_per_launch * 1.5 / (scan_ms * 1e-3)) / mix,
-                "probe_thread_inst_per_s": {"imad": imad, "vabsdiff4": sad, "vimnmx3": mnmx, "match_mix": mix},
+                "achieved": pairs_per_s / 1e12, "peak": sad / 1e12, "unit": "T pairs/s", "frac": pairs_per_s / sad,
+                "traffic": measured_traffic("match_kernel", world),
+                "note": "the same step with EMO_MATCH_SCAN (the north star's brute-force kernel): achieved = (query, candidate) "
+                        "pairs per second of the scan launch; peak = VABSDIFF4 issue rate measured in this run "
+                        "(tools/probe/probe.cu): one VABSDIFF4.U8.ACC per pair is the floor for a 3-byte vector; the ncu "
+                        "capture in profiles/ shows the ALU pipe 97.8 % active (VABSDIFF4 + VIMNMX3 share it)",
+                "algorithmic_int_ops_per_s": 2 * D * pairs_per_s,
+                "probe_thread_inst_per_s": probes,
             },
         }
+        if comm is not None:
+            extra["comm"] = dict(comm, library_replication="emo_comm_set_library_dev (ncclBroadcast inside libemosaic_cuda.so)")
+        if c2 is not None:
+            extra["c2_4to1"] = c2
         if world == 1 and not args.no_extras:
             extra.update(extras(ctx, torch, dev, hbm_peak, peak_src))
-            c2 = extra.get("c2_4to1", {})
-            if "match_ms" in c2 and sad > 0:  # C2 (BASELINE configs[1]): the 4to1 scan against the VABSDIFF4 rate measured in this run
-                pairs2 = (1024 // 2) ** 2 * 20000
-                c2["roofline"] = {"kernel": "match_kernel<3,2,128>", "bound": "int32-pipe (VABSDIFF4)", "unit": "T abs-diff-words/s",
-                                  "achieved": 3 * pairs2 / (c2["match_ms"] * 1e-3) / 1e12, "peak": sad / 1e12,
-                                  "frac": 3 * pairs2 / (c2["match_ms"] * 1e-3) / sad, "traffic": None,
-                                  "note": "3 VABSDIFF4 per (block, candidate) pair (12 bytes); the inner loop's IMAD / VIMNMX3 share "
-                                          "caps the fraction at 0.92"}
         if c3_sharded is not None:
             extra["c3_analysis_sharded"] = c3_sharded
         if weak is not None:
             extra["weak_scaling"] = weak
+        if group_e2e is not None:
+            extra["e2e_single_process_group"] = group_e2e
         cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
         if cpu is not None:
             extra["cpu_baseline_spread_library"] = cpu_baseline_spread(cfg)
+        d2h_bytes = H * ts * W * ts * 3
+        e2e = {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": d2h_bytes,
+               "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "api": "emo_mosaic (host pointers, pinned), one call per rank on its stripe",
+               "d2h_gbs": d2h_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9}
+        if host is not None:
+            e2e["host_d2h_ceiling_gbs"] = host["d2h_all_ranks_gbs"]
+            e2e["frac_of_host_ceiling"] = e2e["d2h_gbs"] / host["d2h_all_ranks_gbs"]
+            e2e["host_ceiling"] = host
         line = {
             "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tiles": T, "tile_size": ts, "source": [H, W], "mode": "1to1",
-                       "match": "colour-cube index lookup (exact; built once per library, extra.index_build_ms); "
-                                "brute-force scan of the same step in extra.match_scan",
+                       "match": "colour-cube index lookup (exact; built once per library, extra.index_build_ms; per-render figure "
+                                "in extra.value_per_render); brute-force scan of the same step in extra.match_scan",
                        "parallelism": f"row-stripes x{world}", "rows_per_rank": Hs,
                        "l2": "no explicit flush: every step writes a 3.2 GB/N output stripe and re-reads 50 MB/N of source, "
                              "far more than the 126 MB L2", "gpu": info["name"]},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": H * ts * W * ts * 3,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "api": "emo_mosaic (host pointers, pinned)"},
+            "e2e": e2e,
             "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
     if world > 1:
@@ -457,52 +519,161 @@ def run_ours(args):
     ctx.close()
 
 
-def c3_across_ranks(ctx, torch, dist, dev, world, rank, max_over_ranks, barrier):
-    """C3 (analysis cache build, 1M tiles of 64x64, fused 1to1+4to1) sharded over the ranks (SURVEY §8e): every rank analyses
-    its contiguous range of tiles, one NCCL all_gather per output assembles [T,3] and [T,12] on every rank.  Timed on the
-    device (kernel + collectives on one stream), max over ranks.  Outside the timed region of the headline number."""
-    from emosaic_b200 import sharding
-    T3, ts3 = 1_000_000, 64
-    a, b = sharding.stripe_bounds(T3, world, rank)
-    n = b - a
-    ok = torch.ones(1, device=dev)
+def group_e2e_record(emo, ctx, world, cfg, tiles_h, colors_h, src_h):
+    """The whole C4 image through ONE process: emo_group_mosaic over `world` GPUs, host buffers pinned, every GPU copying its
+    stripe to its row offset of one output image.  Timed with CUDA events on every member's stream (max over members)."""
+    T, ts, W, H = cfg["T"], cfg["ts"], cfg["W"], cfg["H"]
+    g = emo.Group(list(range(world)))
     try:
-        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-        tiles = torch.randint(0, 256, (n * ts3 * ts3 * 3,), dtype=torch.uint8, device=dev, generator=g)
-        o1 = torch.empty(n * 3, dtype=torch.uint8, device=dev)
-        o4 = torch.empty(n * 12, dtype=torch.uint8, device=dev)
-    except Exception:  # noqa: BLE001  (e.g. out of memory on one rank: nobody enters the collective)
-        ok.zero_()
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if float(ok.item()) == 0.0:
-        return {"error": "allocation failed on a rank"}
-    stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream that both torch/NCCL and the library can use
-    torch.cuda.synchronize()
-    ctx.sync()
-    ctx.set_stream(stream.cuda_stream)          # kernel and collectives on one stream, bracketed by one pair of events
-    times, k_times = [], []
-    try:
-        with torch.cuda.stream(stream):
-            for rep in range(4):
-                barrier()
-                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-                e0.record(stream)
-                ctx.analyse_fused_dev(tiles.data_ptr(), n, ts3, o1.data_ptr(), o4.data_ptr())
-                e1.record(stream)
-                f1 = sharding.gather_analysis(o1, T3, 3, world, rank)
-                f4 = sharding.gather_analysis(o4, T3, 12, world, rank)
-                e2.record(stream)
-                torch.cuda.synchronize()
-                if rep:                                   # first pass warms NCCL up
-                    times.append(max_over_ranks(e0.elapsed_time(e2)))
-                    k_times.append(max_over_ranks(e0.elapsed_time(e1)))
-            same = bool((f1[a * 3:b * 3] == o1).all()) and bool((f4[a * 12:b * 12] == o4).all()) and f1.numel() == T3 * 3
+        g.set_library(colors_h, tiles_h)
+        src_pin = ctx.host_alloc(H * W * 3)
+        out_pin = ctx.host_alloc(H * ts * W * ts * 3)
+        src_pin[:] = src_h.reshape(-1)
+        src_img, out_img = src_pin.reshape(H, W, 3), out_pin.reshape(H * ts, W * ts, 3)
+        g.mosaic(src_img, 3, 0, out=out_img, want_maps=False)      # warm-up: staging buffers, index build on every GPU
+        steps = 3
+        for m in g.members:
+            m.timer_start()
+        for _ in range(steps):
+            g.mosaic(src_img, 3, 0, out=out_img, want_maps=False)
+        ms = max(m.timer_stop() for m in g.members)
+        # same bytes as one GPU: the first and the last 8 block rows against rank 0's own ctx (same library resident)
+        top, _, _ = ctx.mosaic(src_img[:8], 3, 0, want_maps=False)
+        bot, _, _ = ctx.mosaic(src_img[H - 8:], 3, 0, want_maps=False)
+        ok = bool((out_img[:8 * ts] == top).all() and (out_img[(H - 8) * ts:] == bot).all())
+        rec = {"value": H * W * steps / (ms * 1e-3), "unit": "px/s", "ms_per_step": ms / steps, "gpus": world,
+               "d2h_gbs": H * ts * W * ts * 3 / (ms / steps * 1e-3) / 1e9, "api": "emo_group_mosaic (one process, one worker thread per GPU)",
+               "same_bytes_as_one_gpu": ok}
+        ctx.host_free(src_pin)
+        ctx.host_free(out_pin)
+        return rec
     finally:
-        torch.cuda.synchronize()
-        ctx.set_stream(None)
+        g.close()
+
+
+def c2_record(ctx, emo, torch, dev, world, rank, args, max_over_ranks, barrier, sad_rate):
+    """C2 = BASELINE configs[1]: 4to1 (--mode 2 -s 16), 10k synthetic tiles, 1024x1024 source -> 8192x8192x3; block rows
+    sharded over the ranks like the headline, library replicated from rank 0 by emo_comm_set_library.  `value` resident,
+    `e2e` through emo_mosaic with pinned host buffers; the scan kernel against the VABSDIFF4 issue rate."""
+    T2, ts2, S2, dim = 10_000, 16, 1024, 2
+    if rank == 0:
+        tiles = np.random.default_rng(1234).integers(0, 256, (T2, ts2, ts2, 3), dtype=np.uint8)
+        ctx.comm_set_library(ctx.analyse_tiles(tiles, dim), tiles, root=0)
+    else:
+        ctx.comm_set_library(None, None, root=0)
+    src = np.random.default_rng(5678).integers(0, 256, (S2, S2, 3), dtype=np.uint8)
+    bh = bw = S2 // dim
+    a, b = emo.stripe_bounds(bh, world, rank)
+    rows = b - a
+    stripe = np.ascontiguousarray(src[a * dim:b * dim])
+    src_d = torch.from_numpy(stripe.reshape(-1)).to(dev)
+    item_d = torch.empty(max(rows * bw, 1), dtype=torch.int32, device=dev)
+    dist_d = torch.empty(max(rows * bw, 1), dtype=torch.int32, device=dev)
+    out_d = torch.empty(max(rows * ts2 * bw * ts2 * 3, 1), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    base = 40000
+
+    def step(k=None):
+        if rows == 0:
+            return
+        if k is not None:
+            ctx.mark(base + 3 * k)
+        ctx.match_dev(src_d.data_ptr(), S2, rows * dim, item_d.data_ptr(), dist_d.data_ptr())
+        if k is not None:
+            ctx.mark(base + 3 * k + 1)
+        ctx.compose_dev(item_d.data_ptr(), 0, S2, rows * dim, 3, 0, out_d.data_ptr())
+        if k is not None:
+            ctx.mark(base + 3 * k + 2)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.sync()
+    barrier()
+    ctx.timer_start()
+    for k in range(args.steps):
+        step(k)
+    ms = ctx.timer_stop()
+    barrier()
+    ms = max_over_ranks(ms)
+    m_ms = float(np.mean([ctx.mark_elapsed(base + 3 * k, base + 3 * k + 1) for k in range(args.steps)])) if rows else 0.0
+    c_ms = float(np.mean([ctx.mark_elapsed(base + 3 * k + 1, base + 3 * k + 2) for k in range(args.steps)])) if rows else 0.0
+    m_ms_max, c_ms_max = max_over_ranks(m_ms), max_over_ranks(c_ms)
+    # e2e: host stripe in, host stripe out
+    e2e_steps = 3
+    src_pin = ctx.host_alloc(max(stripe.nbytes, 1))
+    out_pin = ctx.host_alloc(max(rows * ts2 * bw * ts2 * 3, 1))
+    src_pin[:stripe.nbytes] = stripe.reshape(-1)
+    if rows:
+        s_img = src_pin[:stripe.nbytes].reshape(rows * dim, S2, 3)
+        o_img = out_pin.reshape(rows * ts2, bw * ts2, 3)
+        ctx.mosaic(s_img, 3, 0, out=o_img, want_maps=False)
+    barrier()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        if rows:
+            ctx.mosaic(s_img, 3, 0, out=o_img, want_maps=False)
+    e_ms = ctx.timer_stop()
+    barrier()
+    e_ms = max_over_ranks(e_ms)
+    same = True
+    if rows:
+        same = bool((torch.from_numpy(out_pin[:1 << 20].copy()).to(dev) == out_d[:1 << 20]).all())
+    ctx.host_free(src_pin)
+    ctx.host_free(out_pin)
+    pairs = rows * bw * 2 * T2                               # this rank's (block, candidate) pairs per launch
+    rec = {
+        "workload": "C2: 4to1 (--mode 2 -s 16), 10k synthetic 16x16 tiles, 1024x1024 source -> 8192x8192x3, row-sharded",
+        "metric": "matched source px/s (4to1, match+compose, whole job)", "value": S2 * S2 * args.steps / (ms * 1e-3), "unit": "px/s",
+        "n_gpus": world, "ms_per_step": ms / args.steps, "match_ms": m_ms_max, "compose_ms": c_ms_max,
+        "composed_output_gbs": bh * ts2 * bw * ts2 * 3 / (c_ms_max * 1e-3) / 1e9 if c_ms_max else None,
+        "e2e": {"value": S2 * S2 * e2e_steps / (e_ms * 1e-3), "unit": "px/s", "ms_per_step": e_ms / e2e_steps,
+                "h2d_bytes_per_step": S2 * S2 * 3, "d2h_bytes_per_step": bh * ts2 * bw * ts2 * 3, "api": "emo_mosaic (host pointers, pinned)",
+                "same_bytes_as_resident_path": same},
+    }
+    if sad_rate and m_ms:
+        rec["roofline"] = {"kernel": "match_kernel<3,...> (scan, D = 12)", "bound": "int32-pipe (VABSDIFF4)", "unit": "T abs-diff-words/s",
+                           "achieved": 3 * pairs / (m_ms * 1e-3) / 1e12, "peak": sad_rate / 1e12, "frac": 3 * pairs / (m_ms * 1e-3) / sad_rate,
+                           "traffic": measured_traffic("match_kernel_c2", world), "ms_per_launch": m_ms,
+                           "note": "3 VABSDIFF4 per (block, candidate) pair (12 bytes) on rank 0's stripe; peak = VABSDIFF4 issue rate "
+                                   "measured in this run"}
+    return rec
+
+
+def c3_across_ranks(ctx, emo, torch, dev, world, rank, max_over_ranks, barrier):
+    """C3 (analysis cache build, 1M tiles of 64x64, fused 1to1+4to1) sharded over the ranks (SURVEY §8e): every rank analyses
+    its contiguous range of tiles, emo_comm_allgather_analysis_dev (ncclAllGather inside libemosaic_cuda.so) assembles [T,3]
+    and [T,12] on every rank.  Kernel and collectives run on the ctx stream, timed with its CUDA events, max over ranks.
+    Outside the timed region of the headline number."""
+    T3, ts3 = 1_000_000, 64
+    a, b = emo.stripe_bounds(T3, world, rank)
+    n = b - a
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    tiles = torch.randint(0, 256, (n * ts3 * ts3 * 3,), dtype=torch.uint8, device=dev, generator=g)
+    o1 = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+    o4 = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+    f1 = torch.empty(T3 * 3, dtype=torch.uint8, device=dev)
+    f4 = torch.empty(T3 * 12, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    times, k_times = [], []
+    for rep in range(4):
+        barrier()
+        ctx.mark(50000)
+        ctx.analyse_fused_dev(tiles.data_ptr(), n, ts3, o1.data_ptr(), o4.data_ptr())
+        ctx.mark(50001)
+        ctx.comm_allgather_analysis_dev(o1.data_ptr(), T3, 3, f1.data_ptr())
+        ctx.comm_allgather_analysis_dev(o4.data_ptr(), T3, 12, f4.data_ptr())
+        ctx.mark(50002)
+        ctx.sync()
+        if rep:                                   # first pass warms NCCL up
+            times.append(max_over_ranks(ctx.mark_elapsed(50000, 50002)))
+            k_times.append(max_over_ranks(ctx.mark_elapsed(50000, 50001)))
+    same = bool((f1[a * 3:b * 3] == o1).all()) and bool((f4[a * 12:b * 12] == o4).all())
     ms, kms = float(np.median(times)), float(np.median(k_times))
+    del tiles, o1, o4, f1, f4
+    torch.cuda.empty_cache()
     return {"tiles": T3, "ranks": world, "ms": ms, "kernel_ms": kms, "allgather_ms": ms - kms, "tiles_per_s": T3 / (ms * 1e-3),
-            "input_gbs_whole_job": T3 * 12303 / (ms * 1e-3) / 1e9, "own_range_intact_after_gather": same}
+            "input_gbs_whole_job": T3 * 12303 / (ms * 1e-3) / 1e9, "own_range_intact_after_gather": same,
+            "collective": "emo_comm_allgather_analysis_dev (ncclAllGather, libemosaic_cuda.so)"}
 
 
 def extras(ctx, torch, dev, hbm_peak, peak_src):
@@ -561,26 +732,6 @@ def extras(ctx, torch, dev, hbm_peak, peak_src):
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         ex["c5_tint"] = {"error": str(e)}
-
-    # C2: 4to1, 10k tiles, ts 16, 1024x1024 source (D = 12, L = 20 000)
-    try:
-        T2, ts2, S2 = 10_000, 16, 1024
-        tiles2 = torch.from_numpy(np.random.default_rng(1234).integers(0, 256, (T2 * ts2 * ts2 * 3,), dtype=np.uint8)).to(dev)
-        src2 = torch.from_numpy(np.random.default_rng(5678).integers(0, 256, (S2 * S2 * 3,), dtype=np.uint8)).to(dev)
-        col2 = torch.empty(T2 * 12, dtype=torch.uint8, device=dev)
-        Q2 = (S2 // 2) * (S2 // 2)
-        item2 = torch.empty(Q2, dtype=torch.int32, device=dev)
-        dist2 = torch.empty(Q2, dtype=torch.int32, device=dev)
-        out2 = torch.empty((S2 // 2) * ts2 * (S2 // 2) * ts2 * 3, dtype=torch.uint8, device=dev)
-        torch.cuda.synchronize()
-        ctx.analyse_dev(tiles2.data_ptr(), T2, ts2, 2, col2.data_ptr())
-        ctx.set_library_dev(col2.data_ptr(), tiles2.data_ptr(), T2, 4, ts2)
-        m_ms = timeit(lambda: ctx.match_dev(src2.data_ptr(), S2, S2, item2.data_ptr(), dist2.data_ptr()))
-        c_ms = timeit(lambda: ctx.compose_dev(item2.data_ptr(), 0, S2, S2, 3, 0, out2.data_ptr()))
-        ex["c2_4to1"] = {"match_ms": m_ms, "compose_ms": c_ms, "matched_source_px_per_s": S2 * S2 / (m_ms * 1e-3),
-                         "int_ops_per_s": 2 * 12 * Q2 * 2 * T2 / (m_ms * 1e-3)}
-    except Exception as e:  # noqa: BLE001
-        ex["c2_4to1"] = {"error": str(e)}
 
     # Lanczos3 resize (image 0.25.2 imageops::resize, bit-exact): the source step of main.rs:567-595 on a C4-sized image that is
     # not divisible (4098 x 4097 -> 4096 x 4096) and tile preparation (tiles/utils.rs:188-189) of 64 photos of 2048^2 -> 64^2.

@@ -15,10 +15,15 @@ EXPORTS = [
     "emo_abi_version", "emo_last_error", "emo_create", "emo_destroy", "emo_set_stream", "emo_sync",
     "emo_device_info", "emo_launch_count", "emo_timer_start", "emo_timer_stop", "emo_mark", "emo_mark_elapsed", "emo_dev_alloc", "emo_dev_free",
     "emo_host_alloc", "emo_host_free", "emo_copy_h2d", "emo_copy_d2h", "emo_analyse", "emo_analyse_dev",
-    "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_build_index",
+    "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_library_info", "emo_build_index",
     "emo_set_match_mode", "emo_match", "emo_topk", "emo_topk_dev",
     "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev",
-    "emo_probe_int_pipe", "emo_resize", "emo_resize_dev", "emo_resize_taps",
+    "emo_resize", "emo_resize_dev", "emo_resize_taps",
+    "emo_stripe_bounds", "emo_host_register", "emo_host_unregister",
+    "emo_comm_unique_id", "emo_comm_init_rank", "emo_comm_info", "emo_comm_set_library", "emo_comm_set_library_dev",
+    "emo_comm_broadcast_dev", "emo_comm_allgather_analysis_dev",
+    "emo_group_create", "emo_group_destroy", "emo_group_size", "emo_group_ctx", "emo_group_set_library", "emo_group_analyse",
+    "emo_group_analyse_fused", "emo_group_mosaic",
 ]
 
 _lib = None
@@ -66,6 +71,7 @@ def load() -> C.CDLL:
         "emo_analyse_fused_dev": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint32, u8p, u8p]),
         "emo_set_library": (C.c_int, [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_uint32]),
         "emo_set_library_dev": (C.c_int, [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_uint32]),
+        "emo_library_info": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "emo_build_index": (C.c_int, [vp]),
         "emo_set_match_mode": (C.c_int, [vp, C.c_int]),
         "emo_match": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
@@ -78,10 +84,27 @@ def load() -> C.CDLL:
         "emo_compose_overlay_dev": (C.c_int, [vp, i32p, C.c_uint32, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_mosaic": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
         "emo_mosaic_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
-        "emo_probe_int_pipe": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
         "emo_resize": (C.c_int, [vp, u8p] + [C.c_uint32] * 9 + [u8p]),
         "emo_resize_dev": (C.c_int, [vp, u8p] + [C.c_uint32] * 9 + [u8p]),
         "emo_resize_taps": (C.c_int, [C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "emo_stripe_bounds": (None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "emo_host_register": (C.c_int, [vp, C.c_size_t]),
+        "emo_host_unregister": (C.c_int, [vp]),
+        "emo_comm_unique_id": (C.c_int, [vp]),
+        "emo_comm_init_rank": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "emo_comm_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "emo_comm_set_library": (C.c_int, [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+        "emo_comm_set_library_dev": (C.c_int, [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+        "emo_comm_broadcast_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
+        "emo_comm_allgather_analysis_dev": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint32, u8p]),
+        "emo_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "emo_group_destroy": (None, [vp]),
+        "emo_group_size": (C.c_int, [vp]),
+        "emo_group_ctx": (vp, [vp, C.c_int]),
+        "emo_group_set_library": (C.c_int, [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_uint32]),
+        "emo_group_analyse": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]),
+        "emo_group_analyse_fused": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint32, u8p, u8p]),
+        "emo_group_mosaic": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the export is missing

@@ -48,10 +48,14 @@ MATCH_MODES = {"auto": MATCH_AUTO, "scan": MATCH_SCAN, "index": MATCH_INDEX}
 class Context:
     """One per GPU (one process per GPU under torchrun).  Wraps ``emo_ctx``."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None):
         self._lib = _lib.load()
-        h = C.c_void_p()
-        check(self._lib.emo_create(int(device), C.byref(h)))
+        self._owned = _handle is None
+        if _handle is None:
+            h = C.c_void_p()
+            check(self._lib.emo_create(int(device), C.byref(h)))
+        else:  # a member of a Group: the group owns the emo_ctx
+            h = C.c_void_p(_handle)
         self._h = h
         self.device = device
         self.N = 0
@@ -61,7 +65,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.emo_destroy(self._h)
+            if self._owned:
+                self._lib.emo_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -128,10 +133,58 @@ class Context:
     def d2h(self, dst: np.ndarray, src: int):
         check(self._lib.emo_copy_d2h(self._h, _ptr(dst), C.c_void_p(src), dst.nbytes))
 
-    def probe_int_pipe(self, which: int) -> float:
-        v = C.c_double()
-        check(self._lib.emo_probe_int_pipe(self._h, which, C.byref(v)))
-        return float(v.value)
+    # -- multi-GPU, one process per GPU (include/emosaic_cuda.h "multi-GPU" (a)) -----------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId: 128 bytes rank 0 hands to every rank (torchrun's store, a file, ...)."""
+        buf = C.create_string_buffer(128)
+        check(_lib.load().emo_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, uid: bytes, rank: int, world: int):
+        if len(uid) != 128:
+            raise EmosaicError(EMO_ERR_ARG, f"the communicator id has 128 bytes, got {len(uid)}")
+        check(self._lib.emo_comm_init_rank(self._h, C.c_char_p(uid), rank, world))
+        self.rank, self.world = rank, world
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.emo_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def comm_set_library(self, colors=None, tile_px=None, root: int = 0):
+        """emo_set_library on every rank from the root's arrays (NCCL broadcast); the other ranks pass nothing."""
+        T = N = ts = 0
+        if colors is not None:
+            colors = _u8(colors)
+            if colors.ndim != 3 or colors.shape[2] != 3:
+                raise EmosaicError(EMO_ERR_ARG, f"colors must be [T,N,3], got {colors.shape}")
+            T, N = colors.shape[:2]
+            if tile_px is not None:
+                tile_px = _u8(tile_px)
+                ts = tile_px.shape[1]
+        check(self._lib.emo_comm_set_library(self._h, _ptr(colors), _ptr(tile_px), T, N, ts, root))
+        self._refresh_library_info()
+
+    def comm_set_library_dev(self, colors_dev: int, tile_px_dev: int, T: int, N: int, ts: int, root: int = 0):
+        check(self._lib.emo_comm_set_library_dev(self._h, C.c_void_p(colors_dev or 0), C.c_void_p(tile_px_dev or 0), T, N, ts, root))
+        self._refresh_library_info()
+
+    def library_info(self):
+        """(T, N, ts) of the resident library (zeros when none)."""
+        T, N, ts = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(self._lib.emo_library_info(self._h, C.byref(T), C.byref(N), C.byref(ts)))
+        return T.value, N.value, ts.value
+
+    def _refresh_library_info(self):
+        self.T, self.N, self.ts = self.library_info()
+        self.dim = _isqrt_exact(self.N) if self.N else 0
+
+    def comm_broadcast_dev(self, buf_dev: int, nbytes: int, root: int = 0):
+        check(self._lib.emo_comm_broadcast_dev(self._h, C.c_void_p(buf_dev), nbytes, root))
+
+    def comm_allgather_analysis_dev(self, local_dev: int, T: int, bytes_per_tile: int, all_dev: int):
+        check(self._lib.emo_comm_allgather_analysis_dev(self._h, C.c_void_p(local_dev or 0), T, bytes_per_tile, C.c_void_p(all_dev)))
 
     # -- (0) Lanczos3 resize --------------------------------------------------------------
     def resize(self, images, nw: int, nh: int, view=None) -> np.ndarray:
@@ -295,6 +348,126 @@ class Context:
         dist = np.zeros((bh, bw), np.uint32) if want_maps else None
         check(self._lib.emo_mosaic(self._h, _ptr(src), W, H, out_channels, tint_alpha, _ptr(item), _ptr(dist), _ptr(out)))
         return out, item, dist
+
+
+def stripe_bounds(units: int, world: int, rank: int):
+    """emo_stripe_bounds: the contiguous [start, stop) of `units` block rows / tiles that part `rank` of `world` owns."""
+    a, b = C.c_uint64(), C.c_uint64()
+    _lib.load().emo_stripe_bounds(units, world, rank, C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+class Group:
+    """Several GPUs driven from one process (``emo_group``): the library is replicated with one NCCL broadcast, the
+    source's block rows (rendering.rs:68-89) / the library's tiles (main.rs:760-794) are split into contiguous ranges, and
+    every GPU copies its stripe of the result straight into the caller's array.  Same results as one ``Context``."""
+
+    def __init__(self, devices: Sequence[int] | int = 1):
+        self._lib = _lib.load()
+        if isinstance(devices, int):
+            devices = list(range(devices))
+        devices = [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(self._lib.emo_group_create(arr, len(devices), C.byref(h)))
+        self._h = h
+        self.devices = devices
+        self.members = [Context(d, _handle=self._lib.emo_group_ctx(h, i)) for i, d in enumerate(devices)]
+        self.N = self.dim = self.ts = self.T = 0
+
+    def __len__(self):
+        return len(self.devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for m in self.members:
+                m.close()
+            self._lib.emo_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        for m in self.members:
+            m.sync()
+
+    def launch_count(self) -> int:
+        return sum(m.launch_count() for m in self.members)
+
+    def set_match_mode(self, mode):
+        for m in self.members:
+            m.set_match_mode(mode)
+
+    def set_library(self, colors, tile_px=None):
+        colors = _u8(colors)
+        if colors.ndim != 3 or colors.shape[2] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"colors must be [T,N,3], got {colors.shape}")
+        T, N = colors.shape[:2]
+        ts = 0
+        if tile_px is not None:
+            tile_px = _u8(tile_px)
+            if tile_px.ndim != 4 or tile_px.shape[0] != T or tile_px.shape[1] != tile_px.shape[2] or tile_px.shape[3] != 3:
+                raise EmosaicError(EMO_ERR_ARG, f"tile_px must be [T,ts,ts,3] with T={T}, got {tile_px.shape}")
+            ts = tile_px.shape[1]
+        check(self._lib.emo_group_set_library(self._h, _ptr(colors), _ptr(tile_px), T, N, ts))
+        self.T, self.N, self.dim, self.ts = T, N, _isqrt_exact(N), ts
+        for m in self.members:
+            m.T, m.N, m.dim, m.ts = self.T, self.N, self.dim, self.ts
+
+    def analyse_tiles(self, tiles, dim: int) -> np.ndarray:
+        tiles = _u8(tiles)
+        if tiles.ndim != 4 or tiles.shape[1] != tiles.shape[2] or tiles.shape[3] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"tiles must be [T,ts,ts,3], got {tiles.shape}")
+        T, ts = tiles.shape[:2]
+        out = np.zeros((T, dim * dim, 3), np.uint8)
+        check(self._lib.emo_group_analyse(self._h, _ptr(tiles), T, ts, dim, _ptr(out)))
+        return out
+
+    def analyse_tiles_fused(self, tiles):
+        tiles = _u8(tiles)
+        T, ts = tiles.shape[:2]
+        o1 = np.zeros((T, 1, 3), np.uint8)
+        o4 = np.zeros((T, 4, 3), np.uint8)
+        check(self._lib.emo_group_analyse_fused(self._h, _ptr(tiles), T, ts, _ptr(o1), _ptr(o4)))
+        return o1, o4
+
+    def mosaic(self, src, out_channels: int = 3, tint_alpha: int = 0, out: np.ndarray | None = None, want_maps=True):
+        src = _u8(src)
+        H, W = src.shape[:2]
+        d = max(self.dim, 1)
+        bh, bw = H // d, W // d
+        if out is None:
+            out = np.zeros((bh * self.ts, bw * self.ts, out_channels), np.uint8)
+        item = np.zeros((bh, bw), np.int32) if want_maps else None
+        dist = np.zeros((bh, bw), np.uint32) if want_maps else None
+        check(self._lib.emo_group_mosaic(self._h, _ptr(src), W, H, out_channels, tint_alpha, _ptr(item), _ptr(dist), _ptr(out)))
+        return out, item, dist
+
+    # single-GPU services a renderer needs besides the sharded calls run on the first member
+    def resize(self, *a, **k):
+        return self.members[0].resize(*a, **k)
+
+    def compose(self, *a, **k):
+        return self.members[0].compose(*a, **k)
+
+    def compose_overlay(self, *a, **k):
+        return self.members[0].compose_overlay(*a, **k)
+
+    def topk(self, *a, **k):
+        return self.members[0].topk(*a, **k)
+
+
+def host_register(arr: np.ndarray):
+    """Pin an existing host array (cudaHostRegister) so the per-GPU copies of the group calls run at full PCIe rate."""
+    check(_lib.load().emo_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+
+def host_unregister(arr: np.ndarray):
+    check(_lib.load().emo_host_unregister(C.c_void_p(arr.ctypes.data)))
 
 
 _default_ctx: Optional[Context] = None

@@ -40,6 +40,24 @@ def find_images(root: str, extensions) -> List[str]:
     return out
 
 
+def prepare_tiles(paths: List[str], tile_size: int, crop: bool, ctx, root: str = ""):
+    """The tile loop of generate_tile_set (main.rs:757-806): a file that cannot be decoded or prepared (too small, no
+    non-white interior, corrupt) is collected, listed and left out; the survivors keep their order, so idx numbering matches
+    the reference.  Returns (pixels [T,ts,ts,3], surviving paths)."""
+    px, ok, failed = [], [], []
+    for p in paths:
+        try:
+            px.append(prepare_tile(p, tile_size, crop, ctx))
+            ok.append(p)
+        except (api.EmosaicError, OSError, ValueError, SyntaxError, EOFError) as e:   # PIL raises OSError / SyntaxError / ValueError
+            failed.append((os.path.relpath(p, root) if root else p, e))
+    if failed:
+        print(f"Failed to read the following images({len(failed)}):", file=sys.stderr)
+        for p, e in failed:
+            print(f"- {p}: {e}", file=sys.stderr)
+    return (np.stack(px) if px else np.zeros((0, tile_size, tile_size, 3), np.uint8)), ok
+
+
 def prepare_tile(path: str, tile_size: int, crop: bool, ctx: Optional[api.Context] = None) -> np.ndarray:
     """tiles/utils.rs:63-196 without the JPEG cache: decode (host), then trim view / crop / Lanczos3 resize (GPU) / rotate."""
     from PIL import Image
@@ -69,6 +87,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("-o", "--output-path", default="./output.jpg")
     p.add_argument("--crop", action="store_true")
     p.add_argument("--device", type=int, default=0)
+    p.add_argument("--gpus", type=int, default=1, help="split the work over GPUs 0..N-1 of this box (row stripes of the source, "
+                   "tile ranges of the analysis build; the library is replicated with one NCCL broadcast)")
     p.add_argument("img")
     sub = p.add_subparsers(dest="subcmd")
     sub.add_parser("prepare")
@@ -133,13 +153,20 @@ def main(argv=None) -> int:
     mode = MODES[args.mode]
     print(f"Opening source image: {args.img}", file=sys.stderr)
     original = np.asarray(Image.open(args.img).convert("RGB"), dtype=np.uint8)
-    ctx = api.Context(args.device)
+    if args.gpus < 1:
+        print("error: --gpus must be at least 1", file=sys.stderr)
+        return 2
+    # one GPU: a Context; several: a Group (same interface for analyse_tiles / set_library / mosaic, sharded inside)
+    ctx = api.Context(args.device) if args.gpus == 1 else api.Group(args.gpus)
     exts = set(args.extensions)
 
     if mode == "random":  # main.rs:414-442 + rendering.rs:418-440: uniform random tile per source pixel
         paths = [p for p in find_images(args.tiles_dir, exts) if os.path.exists(p)]
         print(f"Tile set with {len(paths)} tiles", file=sys.stderr)
-        px = np.stack([prepare_tile(p, ts, True, ctx) for p in paths])
+        px, paths = prepare_tiles(paths, ts, True, ctx, args.tiles_dir)
+        if len(paths) == 0:
+            print("error: no tiles", file=sys.stderr)
+            return 1
         ctx.set_library(np.zeros((len(paths), 1, 3), np.uint8), px)
         item = np.random.default_rng(args.seed).integers(1, len(paths) + 1, original.shape[:2]).astype(np.int32)
         out = ctx.compose(item)
@@ -166,11 +193,10 @@ def main(argv=None) -> int:
             try:
                 colors, paths, dates = cache.deserialize_tile_set(open(cache_path, "rb").read(), N, exts, check_exists=True)
                 print("Reusing analysis cache", file=sys.stderr)
-            except ValueError:
+            except (ValueError, MemoryError, OverflowError):  # corrupt cache: re-analyse, like the reference's bincode Err
                 colors = None
         if colors is None:  # generate_tile_set, main.rs:740-813, analysis on the GPU in one batch
-            paths = find_images(args.tiles_dir, exts)
-            px = np.stack([prepare_tile(p, ts, args.crop, ctx) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
+            px, paths = prepare_tiles(find_images(args.tiles_dir, exts), ts, args.crop, ctx, args.tiles_dir)
             dates = [exif_date(p) for p in paths]
             colors = ctx.analyse_tiles(px, dim)
             with open(cache_path, "wb") as f:
@@ -180,7 +206,10 @@ def main(argv=None) -> int:
         # tileset.rs:152-155: a TileSet built by from_tiles holds no images, so rendering always (re)prepares
         # the tiles with crop = true, whatever --crop was used for the analysis
         if px_render is None:
-            px_render = np.stack([prepare_tile(p, ts, True, ctx) for p in paths]) if paths else np.zeros((0, ts, ts, 3), np.uint8)
+            px_render, kept = prepare_tiles(paths, ts, True, ctx, args.tiles_dir)
+            if len(kept) != len(paths):  # tileset.rs:152-155 would fail at the first placement of such a tile (get_image -> Err)
+                print("error: a tile of the analysed set could not be prepared for rendering", file=sys.stderr)
+                return 1
         px = px_render
         print(f"Tile set with {len(paths)} tiles", file=sys.stderr)
         if len(paths) == 0:
@@ -214,7 +243,8 @@ def main(argv=None) -> int:
     Image.fromarray(out).save(args.output_path, format="PNG")  # main.rs:483 save_with_format(Png)
     if dist is not None:
         sp = os.path.splitext(args.output_path)[0] + ".stats.png"
-        Image.fromarray(stats.render(dist, dim, ts)).save(sp, format="PNG")
+        # the no-repeat renderer keys its statistics by output coordinates (rendering.rs:352-365): one pixel per block
+        Image.fromarray(stats.render(dist, ts if args.no_repeat else dim, ts, item != 0)).save(sp, format="PNG")
     return 0
 
 

@@ -95,9 +95,25 @@ struct emo_ctx {
 
     emo_tint_tables tint;
     emo_resize_state *resize = nullptr;
+
+    // multi-GPU (comm.cu): the ctx's NCCL communicator (ncclComm_t), its rank, and a 64-byte device scratch for headers
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    bool comm_owned = false;  // false: the communicator belongs to an emo_group
+    uint32_t *comm_hdr = nullptr;
 };
 
 int emo_ensure(emo_ctx *ctx, void **p, size_t *cap, size_t bytes);  // grow-only device buffer
+void emo_comm_release(emo_ctx *ctx);                                // comm.cu: drops the ctx's communicator (emo_destroy)
+// argument checks and library bookkeeping of ctx.cu, shared with comm.cu
+int emo_check_analyse_args(const void *tiles, uint64_t T, uint32_t ts, uint32_t dim, const void *out);
+int emo_check_library_args(const void *colors, uint32_t T, uint32_t N, uint32_t ts, const void *px);
+int emo_library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, bool has_px);
+// host-pointer pipelines of ctx.cu, shared with the multi-GPU group calls of comm.cu
+int emo_analyse_host_impl(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out1, uint8_t *out4,
+                          bool fused);
+int emo_mosaic_host_impl(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha, int32_t *item,
+                         uint32_t *dist, uint8_t *out, uint64_t total_queries);
 int emo_check_device_flag(emo_ctx *ctx);
 
 // kernels' host launchers (device pointers, async on ctx->stream)

@@ -69,6 +69,8 @@ void emo_destroy(emo_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    emo_comm_release(ctx);
+    cudaFree(ctx->comm_hdr);
     cudaFree(ctx->cand);
     cudaFree(ctx->lib_px);
     cudaFree(ctx->lut);
@@ -191,8 +193,9 @@ int emo_copy_d2h(emo_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes
 int emo_ensure(emo_ctx *ctx, void **p, size_t *cap, size_t bytes) {
     if (*cap >= bytes && *p) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
-    if (*p) {
+    if (*p) {  // both streams may still be working on the old buffer (a pipelined host call that returned on an error)
         EMO_CK(cudaStreamSynchronize(ctx->stream));
+        EMO_CK(cudaStreamSynchronize(ctx->copy_stream));
         EMO_CK(cudaFree(*p));
         *p = nullptr;
         *cap = 0;
@@ -223,7 +226,7 @@ int emo_check_device_flag(emo_ctx *ctx) {
 // ---------------------------------------------------------------------------------------
 // C ABI: device-pointer variants (thin argument checks + launchers) and host-pointer variants
 // ---------------------------------------------------------------------------------------
-static int check_analyse_args(const void *tiles, uint64_t T, uint32_t ts, uint32_t dim, const void *out) {
+int emo_check_analyse_args(const void *tiles, uint64_t T, uint32_t ts, uint32_t dim, const void *out) {
     EMO_REQUIRE(T == 0 || (tiles && out), EMO_ERR_ARG, "analyse: NULL buffer");
     EMO_REQUIRE(ts >= 1 && ts <= 4096, EMO_ERR_ARG, "analyse: tile size %u outside [1,4096]", ts);
     // color.rs:18 "Rectangle dimensions must be positive": floor(ts/dim) == 0 panics in the reference
@@ -236,7 +239,7 @@ extern "C" {
 
 int emo_analyse_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse_dev: ctx is NULL");
-    int rc = check_analyse_args(tiles, T, ts, dim, out);
+    int rc = emo_check_analyse_args(tiles, T, ts, dim, out);
     if (rc) return rc;
     if (T == 0) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
@@ -245,7 +248,7 @@ int emo_analyse_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts,
 
 int emo_analyse_fused_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse_fused_dev: ctx is NULL");
-    int rc = check_analyse_args(tiles, T, ts, 2, out1);
+    int rc = emo_check_analyse_args(tiles, T, ts, 2, out1);
     if (rc) return rc;
     EMO_REQUIRE(T == 0 || out4, EMO_ERR_ARG, "analyse_fused: out4 is NULL");
     EMO_REQUIRE(ts % 2 == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by 2");  // main.rs:612-615
@@ -254,11 +257,13 @@ int emo_analyse_fused_dev(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32
     return emo_launch_analyse_fused(ctx, tiles, T, ts, out1, out4);
 }
 
+}  // extern "C"
+
 // Host-pointer analysis streams the library through two device slabs (~256 MB each): the H2D of slab k+1 runs
 // on the copy stream while slab k is reduced, so a library larger than HBM (or than the caller wants to stage) works
 // and the kernels hide behind PCIe.  dim2 == 0: single analysis into out1; otherwise the fused 1to1 + 4to1 pass.
-static int analyse_host(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out1, uint8_t *out4,
-                        bool fused) {
+int emo_analyse_host_impl(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out1, uint8_t *out4,
+                          bool fused) {
     const size_t tile_b = (size_t)ts * ts * 3;
     const size_t out_per_tile = fused ? 15 : (size_t)dim * dim * 3;
     uint64_t slab_tiles = (256ull << 20) / tile_b;
@@ -294,24 +299,26 @@ static int analyse_host(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t
     return EMO_OK;
 }
 
+extern "C" {
+
 int emo_analyse(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse: ctx is NULL");
-    int rc = check_analyse_args(tiles, T, ts, dim, out);
+    int rc = emo_check_analyse_args(tiles, T, ts, dim, out);
     if (rc) return rc;
     if (T == 0) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
-    return analyse_host(ctx, tiles, T, ts, dim, out, nullptr, false);
+    return emo_analyse_host_impl(ctx, tiles, T, ts, dim, out, nullptr, false);
 }
 
 int emo_analyse_fused(emo_ctx *ctx, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_analyse_fused: ctx is NULL");
-    int rc = check_analyse_args(tiles, T, ts, 2, out1);
+    int rc = emo_check_analyse_args(tiles, T, ts, 2, out1);
     if (rc) return rc;
     EMO_REQUIRE(T == 0 || out4, EMO_ERR_ARG, "analyse_fused: out4 is NULL");
     EMO_REQUIRE(ts % 2 == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by 2");
     if (T == 0) return EMO_OK;
     EMO_CK(cudaSetDevice(ctx->device));
-    return analyse_host(ctx, tiles, T, ts, 2, out1, out4, true);
+    return emo_analyse_host_impl(ctx, tiles, T, ts, 2, out1, out4, true);
 }
 
 // ---- Lanczos3 resize (image 0.25.2 imageops::resize; main.rs:595, tiles/utils.rs:188-189) -----------------------------
@@ -372,20 +379,28 @@ int emo_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t img_w, 
     return EMO_OK;
 }
 
-static int check_library_args(const void *colors, uint32_t T, uint32_t N, uint32_t ts, const void *px) {
+}  // extern "C"
+
+int emo_check_library_args(const void *colors, uint32_t T, uint32_t N, uint32_t ts, const void *px) {
     EMO_REQUIRE(colors, EMO_ERR_ARG, "set_library: colors is NULL");
     EMO_REQUIRE(T >= 1 && T < (1u << 30), EMO_ERR_ARG, "set_library: T=%u outside [1,2^30)", T);
-    uint32_t dim = 1;
+    // --mode 128 (N = 16 384) is the reference's largest (main.rs:403-413); bounding N first keeps the search below in range
+    EMO_REQUIRE(N >= 1 && N <= (1u << 24), EMO_ERR_ARG, "set_library: N=%u outside [1,2^24]", N);
+    uint64_t dim = 1;
     while (dim * dim < N) dim++;
-    EMO_REQUIRE(N >= 1 && dim * dim == N, EMO_ERR_ARG, "set_library: N=%u is not a square", N);
+    EMO_REQUIRE(dim * dim == N, EMO_ERR_ARG, "set_library: N=%u is not a square", N);
     if (px) {
         EMO_REQUIRE(ts >= 1 && ts <= 4096, EMO_ERR_ARG, "set_library: tile size %u outside [1,4096]", ts);
-        EMO_REQUIRE(ts % dim == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by %u", dim);  // main.rs:612-615
+        EMO_REQUIRE(ts % dim == 0, EMO_ERR_ARG, "Invalid tile size: Tile size must be divisible by %u", (uint32_t)dim);  // main.rs:612-615
     }
     return EMO_OK;
 }
 
-static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, bool has_px) {
+extern "C" {
+
+}  // extern "C"
+
+int emo_library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, bool has_px) {
     uint32_t dim = 1;
     while (dim * dim < N) dim++;
     uint32_t words = (3 * N + 3) / 4;
@@ -413,23 +428,25 @@ static int library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, boo
     return EMO_OK;
 }
 
+extern "C" {
+
 int emo_set_library_dev(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_library_dev: ctx is NULL");
-    int rc = check_library_args(colors, T, N, ts, tile_px);
+    int rc = emo_check_library_args(colors, T, N, ts, tile_px);
     if (rc) return rc;
     EMO_CK(cudaSetDevice(ctx->device));
     ctx->T = 0;
-    if ((rc = library_common(ctx, T, N, ts, tile_px != nullptr))) { ctx->T = 0; return rc; }
+    if ((rc = emo_library_common(ctx, T, N, ts, tile_px != nullptr))) { ctx->T = 0; return rc; }
     return emo_launch_build_library(ctx, colors, tile_px);
 }
 
 int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_library: ctx is NULL");
-    int rc = check_library_args(colors, T, N, ts, tile_px);
+    int rc = emo_check_library_args(colors, T, N, ts, tile_px);
     if (rc) return rc;
     EMO_CK(cudaSetDevice(ctx->device));
     ctx->T = 0;
-    if ((rc = library_common(ctx, T, N, ts, tile_px != nullptr))) { ctx->T = 0; return rc; }
+    if ((rc = emo_library_common(ctx, T, N, ts, tile_px != nullptr))) { ctx->T = 0; return rc; }
     size_t cb = (size_t)T * N * 3, pb = tile_px ? (size_t)T * ts * ts * 3 : 0;
     if ((rc = emo_ensure(ctx, &ctx->stage[0], &ctx->stage_cap[0], cb))) return rc;
     EMO_CK(cudaMemcpyAsync(ctx->stage[0], colors, cb, cudaMemcpyHostToDevice, ctx->stream));
@@ -440,6 +457,14 @@ int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px,
     if ((rc = emo_launch_build_library(ctx, (const uint8_t *)ctx->stage[0], tile_px ? (const uint8_t *)ctx->stage[1] : nullptr)))
         return rc;
     EMO_CK(cudaStreamSynchronize(ctx->stream));
+    return EMO_OK;
+}
+
+int emo_library_info(emo_ctx *ctx, uint32_t *T, uint32_t *N, uint32_t *ts) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_library_info: ctx is NULL");
+    if (T) *T = ctx->T;
+    if (N) *N = ctx->T ? ctx->N : 0;
+    if (ts) *ts = (ctx->T && ctx->has_px) ? ctx->ts : 0;
     return EMO_OK;
 }
 
@@ -650,6 +675,15 @@ int emo_mosaic_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uin
 
 int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha,
                int32_t *item, uint32_t *dist, uint8_t *out) {
+    return emo_mosaic_host_impl(ctx, src, W, H, oc, tint_alpha, item, dist, out, 0);
+}
+
+}  // extern "C"
+
+// total_queries: the block count the 1to1 index rule is applied to (0 = this image's own); a multi-GPU caller passes the
+// whole image's count so that every stripe takes the same decision as a single-GPU run would.
+int emo_mosaic_host_impl(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha, int32_t *item,
+                         uint32_t *dist, uint8_t *out, uint64_t total_queries) {
     int rc = check_match_args(ctx, src, W, H);
     if (rc) return rc;
     EMO_REQUIRE(ctx->has_px, EMO_ERR_STATE, "mosaic: no tile pixels resident (emo_set_library with tile_px)");
@@ -677,7 +711,7 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
     uint32_t *ddist = (uint32_t *)ctx->stage[4];
     uint8_t *dout[2] = {(uint8_t *)ctx->stage[5], (uint8_t *)ctx->stage[5] + chunk_out};
     EMO_CK(cudaMemcpyAsync(dsrc, src, sb, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = emo_prepare_match(ctx, Q))) return rc;  // decide on the 1to1 index for the whole image, not per chunk
+    if ((rc = emo_prepare_match(ctx, total_queries ? total_queries : Q))) return rc;  // decide on the 1to1 index for the whole image, not per chunk
     uint32_t k = 0;
     for (uint32_t r0 = 0; r0 < bh; r0 += rows_per_chunk, k++) {
         uint32_t nr = bh - r0 < rows_per_chunk ? bh - r0 : rows_per_chunk;
@@ -699,5 +733,3 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
     EMO_CK(cudaStreamSynchronize(ctx->copy_stream));
     return emo_check_device_flag(ctx);
 }
-
-}  // extern "C"

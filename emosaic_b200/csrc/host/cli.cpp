@@ -1,6 +1,6 @@
 // cli.cpp — `emosaic` with the reference's command line (src/main.rs:28-138) for the accelerated path, C++ host.
 //   emosaic [-s N] [-o PATH] [--crop] IMG mosaic TILES_DIR [-m 1|2|...|128|1to1|4to1|random] [-f] [-t X] [--downsample K]
-//           [--extensions e ...]
+//           [--extensions e ...] [--gpus N]
 //   emosaic [-s N] [-o PATH] [--crop] IMG prepare          (main.rs:380-386: one prepared tile)
 // Tiles and the source are decoded by the minimal PNG/PPM reader of emosaic.cpp (no libjpeg in this image; the Python
 // front end `python -m emosaic_b200` decodes JPEG with PIL).  A tile that is already tile_size x tile_size is taken as
@@ -45,7 +45,7 @@ int main(int argc, char **argv) {
     std::string output = "./output.jpg", img_path, tiles_dir, mode = "1";
     bool crop = false, force = false, mosaic = false, prepare = false, no_repeat = false;
     double tint = 0.0;
-    uint32_t downsample = 1;
+    uint32_t downsample = 1, gpus = 1;
     std::vector<std::string> exts = {"jpg", "jpeg"}, pos;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -58,6 +58,7 @@ int main(int argc, char **argv) {
         else if (a == "-t" || a == "--tint-opacity") tint = std::stod(next());
         else if (a == "--extensions") { exts.clear(); while (i + 1 < argc && argv[i + 1][0] != '-') exts.push_back(argv[++i]); }
         else if (a == "--downsample") downsample = (uint32_t)std::stoul(next());
+        else if (a == "--gpus") gpus = (uint32_t)std::stoul(next());  // row stripes / tile ranges over N GPUs (emo_group)
         else if (a == "--no-repeat") no_repeat = true;  // main.rs:663-664: render_nto1_no_repeat
         else if (a == "--randomize" || a == "--greedy" || a == "--html" || a == "--web") {
             fprintf(stderr, "error: %s is outside the accelerated path\n", a.c_str());
@@ -82,10 +83,13 @@ int main(int argc, char **argv) {
     }
     if (!(tint >= 0.0 && tint <= 1.0)) { fprintf(stderr, "error: Value must be between 0 and 1\n"); return 2; }
     if (downsample < 1) { fprintf(stderr, "error: --downsample must be at least 1\n"); return 2; }
+    if (gpus < 1 || gpus > 64) { fprintf(stderr, "error: --gpus must be between 1 and 64\n"); return 2; }
     img_path = pos[0];
     tiles_dir = pos[1];
     try {
-        Context ctx(0);
+        std::vector<int> devices(gpus);
+        for (uint32_t i = 0; i < gpus; i++) devices[i] = (int)i;
+        Context ctx(devices);
         const Image original = read_image(img_path);
         // tiles/utils.rs:63-196 from the decoded image on; `crop_tile` as prepare_tile's crop argument
         auto load_tile = [&](const std::string &p, bool crop_tile) {
@@ -122,10 +126,23 @@ int main(int argc, char **argv) {
             }
         }
         if (!have) {  // generate_tile_set (main.rs:740-813): one batched analysis on the GPU
-            std::vector<std::string> paths;
-            find_images(tiles_dir, exts, paths);
+            std::vector<std::string> found, paths;
+            find_images(tiles_dir, exts, found);
             std::vector<Image> tiles;
-            for (auto &p : paths) tiles.push_back(load_tile(p, crop));
+            // main.rs:760-806: a tile that cannot be read or prepared is listed and left out; idx numbering follows the survivors
+            std::vector<std::pair<std::string, std::string>> failed;
+            for (auto &p : found) {
+                try {
+                    tiles.push_back(load_tile(p, crop));
+                    paths.push_back(p);
+                } catch (const std::exception &e) {
+                    failed.emplace_back(p.compare(0, tiles_dir.size() + 1, tiles_dir + "/") == 0 ? p.substr(tiles_dir.size() + 1) : p, e.what());
+                }
+            }
+            if (!failed.empty()) {
+                fprintf(stderr, "Failed to read the following images(%zu):\n", failed.size());
+                for (auto &f : failed) fprintf(stderr, "- %s: %s\n", f.first.c_str(), f.second.c_str());
+            }
             const std::vector<uint8_t> colors = analyse_tiles(ctx, tiles, N);
             for (size_t i = 0; i < paths.size(); i++)  // rendering re-prepares with crop = true (tileset.rs:152-155)
                 ts.push_tile_with_image(paths[i], std::vector<uint8_t>(colors.begin() + i * N * 3, colors.begin() + (i + 1) * N * 3),
@@ -147,8 +164,10 @@ int main(int argc, char **argv) {
         summarise(r, ts);
         write_png(output, r.image);
         const size_t dot = output.find_last_of('.');
-        write_png((dot == std::string::npos ? output : output.substr(0, dot)) + ".stats.png", render_stats(r, dim, tile_size));
-    } catch (const Error &e) {
+        // the no-repeat renderer keys its statistics by output coordinates (rendering.rs:352-365): one pixel per block
+        write_png((dot == std::string::npos ? output : output.substr(0, dot)) + ".stats.png",
+                  render_stats(r, no_repeat ? tile_size : dim, tile_size));
+    } catch (const std::exception &e) {
         fprintf(stderr, "error: %s\n", e.what());
         return 1;
     }

@@ -31,9 +31,24 @@ void check(int rc) {
 }
 
 Context::Context(int device) { check(emo_create(device, &h_)); }
-Context::~Context() { emo_destroy(h_); }
-void Context::build_index() const { check(emo_build_index(h_)); }
-void Context::set_match_mode(int mode) const { check(emo_set_match_mode(h_, mode)); }
+Context::Context(const std::vector<int> &devices) {
+    if (devices.size() <= 1) {
+        check(emo_create(devices.empty() ? 0 : devices[0], &h_));
+        return;
+    }
+    check(emo_group_create(devices.data(), (int)devices.size(), &g_));
+    h_ = emo_group_ctx(g_, 0);
+}
+Context::~Context() {
+    if (g_) emo_group_destroy(g_);  // owns its members
+    else emo_destroy(h_);
+}
+void Context::build_index() const {
+    for (int i = 0; i < gpus(); i++) check(emo_build_index(g_ ? emo_group_ctx(g_, i) : h_));
+}
+void Context::set_match_mode(int mode) const {
+    for (int i = 0; i < gpus(); i++) check(emo_set_match_mode(g_ ? emo_group_ctx(g_, i) : h_, mode));
+}
 
 // ---- tiles/utils.rs:18-43 ------------------------------------------------------------------------
 void flipped_coords(std::vector<uint32_t> &coords) {
@@ -66,7 +81,8 @@ std::vector<uint8_t> analyse_tiles(Context &ctx, const std::vector<Image> &tiles
         std::memcpy(px.data() + t * (size_t)ts * ts * 3, tiles[t].data.data(), (size_t)ts * ts * 3);
     }
     std::vector<uint8_t> out((size_t)tiles.size() * N * 3);
-    check(emo_analyse(ctx.handle(), px.data(), tiles.size(), ts, dim, out.data()));
+    if (ctx.group()) check(emo_group_analyse(ctx.group(), px.data(), tiles.size(), ts, dim, out.data()));
+    else check(emo_analyse(ctx.handle(), px.data(), tiles.size(), ts, dim, out.data()));
     return out;
 }
 
@@ -124,7 +140,10 @@ void TileSet::build_kiddo(Context &ctx, uint32_t tile_size) const {
             std::memcpy(&px[t * (size_t)tile_size * tile_size * 3], im.data.data(), (size_t)tile_size * tile_size * 3);
         }
     }
-    check(emo_set_library(ctx.handle(), colors.data(), tile_size ? px.data() : nullptr, (uint32_t)tiles_.size(), N_, tile_size));
+    if (ctx.group())
+        check(emo_group_set_library(ctx.group(), colors.data(), tile_size ? px.data() : nullptr, (uint32_t)tiles_.size(), N_, tile_size));
+    else
+        check(emo_set_library(ctx.handle(), colors.data(), tile_size ? px.data() : nullptr, (uint32_t)tiles_.size(), N_, tile_size));
 }
 
 // ---- rendering.rs ---------------------------------------------------------------------------------
@@ -154,8 +173,12 @@ RenderResult render_nto1(Context &ctx, const Image &source, const TileSet &tile_
     r.image = Image(r.bw * tile_size, r.bh * tile_size, oc);
     r.item.resize((size_t)r.bw * r.bh);
     r.dist.resize((size_t)r.bw * r.bh);
-    check(emo_mosaic(ctx.handle(), source.data.data(), source.width, source.height, oc, tint_alpha(tint_opacity), r.item.data(),
-                     r.dist.data(), r.image.data.data()));
+    if (ctx.group())  // row stripes over the GPUs, each copied to its offset of r.image (rendering.rs:68-101)
+        check(emo_group_mosaic(ctx.group(), source.data.data(), source.width, source.height, oc, tint_alpha(tint_opacity), r.item.data(),
+                               r.dist.data(), r.image.data.data()));
+    else
+        check(emo_mosaic(ctx.handle(), source.data.data(), source.width, source.height, oc, tint_alpha(tint_opacity), r.item.data(),
+                         r.dist.data(), r.image.data.data()));
     return r;
 }
 
@@ -392,8 +415,8 @@ std::vector<uint8_t> serialize_tile_set(const TileSet &ts) {
 
 TileSet deserialize_tile_set(const std::vector<uint8_t> &b, uint32_t N, const std::vector<std::string> *extensions, bool check_exists) {
     size_t pos = 0;
-    auto need = [&](size_t n) {
-        if (pos + n > b.size()) throw Error(EMO_ERR_ARG, "truncated cache file");
+    auto need = [&](uint64_t n) {  // n comes from untrusted u64 lengths: compare without forming pos + n
+        if (n > b.size() - pos) throw Error(EMO_ERR_ARG, "truncated cache file");
     };
     auto get_u64 = [&]() {
         need(8);
@@ -403,12 +426,14 @@ TileSet deserialize_tile_set(const std::vector<uint8_t> &b, uint32_t N, const st
         return v;
     };
     const uint64_t T = get_u64();
+    // every tile costs at least 8 + 3N + 3 bytes here and 8 more in the path list: a corrupt count fails before any allocation
+    if (T > (b.size() - pos) / ((uint64_t)N * 3 + 19)) throw Error(EMO_ERR_ARG, "truncated cache file");
     std::vector<std::vector<uint8_t>> colors;
     std::vector<std::optional<std::string>> dates;
     for (uint64_t t = 0; t < T; t++) {
         const uint64_t ln = get_u64();
         if (ln != (uint64_t)N * 3) throw Error(EMO_ERR_ARG, "cache entry has the wrong vector length");  // try_into().unwrap()
-        need(ln + 3);
+        need(ln + 3);  // ln == 3N was checked above, no overflow
         colors.emplace_back(b.begin() + pos, b.begin() + pos + ln);
         pos += ln + 2;  // stored idx ignored: renumbered below (main.rs:643-652)
         const uint8_t tag = b[pos++];
@@ -447,14 +472,18 @@ TileSet deserialize_tile_set(const std::vector<uint8_t> &b, uint32_t N, const st
 // ---- stats.rs ---------------------------------------------------------------------------------------
 StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print) {
     StatsSummary s;
-    s.total = r.item.size();
+    // rendering.rs:352-365 records placed tiles only: a no-repeat block that ran out of tiles (item 0) has no entry
+    std::vector<size_t> placed;
+    for (size_t i = 0; i < r.item.size(); i++)
+        if (r.item[i] != 0) placed.push_back(i);
+    s.total = placed.size();
     if (!s.total) {
         if (print) fprintf(stderr, "No tiles recorded in statistics\n");
         return s;
     }
     std::map<uint32_t, uint32_t> usage;
     uint64_t sum = 0;
-    for (size_t i = 0; i < r.item.size(); i++) {
+    for (size_t i : placed) {
         usage[(uint32_t)std::abs(r.item[i])]++;
         sum += r.dist[i];
     }
@@ -463,8 +492,7 @@ StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print) {
     std::vector<std::pair<uint32_t, uint32_t>> u(usage.begin(), usage.end());
     std::stable_sort(u.begin(), u.end(), [](auto &a, auto &b) { return a.second > b.second; });
     for (size_t i = 0; i < u.size() && i < 10; i++) s.top.emplace_back(ts.paths().at(u[i].first - 1), u[i].second);
-    std::vector<size_t> order(r.item.size());
-    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::vector<size_t> order = placed;
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return r.dist[a] > r.dist[b]; });
     for (size_t i = 0; i < order.size() && i < 10; i++)
         s.worst.emplace_back(ts.paths().at((size_t)std::abs(r.item[order[i]]) - 1), r.dist[order[i]]);
@@ -481,14 +509,24 @@ StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print) {
 }
 
 Image render_stats(const RenderResult &r, uint32_t dim, uint32_t tile_size) {
-    if (r.item.empty()) throw Error(EMO_ERR_ARG, "Cannot render visualization: no tiles recorded");
+    // `dim` = distance between the recorded coordinates of neighbouring blocks: render_nto1 records SOURCE coordinates
+    // (step = dim, rendering.rs:211-214), render_nto1_no_repeat OUTPUT coordinates (step = tile_size, rendering.rs:352-365)
+    bool any = false;
+    for (int32_t it : r.item) any = any || it != 0;
+    if (!any) throw Error(EMO_ERR_ARG, "Cannot render visualization: no tiles recorded");
     if (tile_size == 0) throw Error(EMO_ERR_ARG, "Tile size must be greater than 0");
-    const uint32_t max_x = (r.bw - 1) * dim, max_y = (r.bh - 1) * dim;
+    uint32_t max_x = 0, max_y = 0, md = 0;
+    for (uint32_t by = 0; by < r.bh; by++)
+        for (uint32_t bx = 0; bx < r.bw; bx++)
+            if (r.item[(size_t)by * r.bw + bx] != 0) {
+                max_x = std::max(max_x, bx * dim);
+                max_y = std::max(max_y, by * dim);
+                md = std::max(md, r.dist[(size_t)by * r.bw + bx]);
+            }
     Image img(max_x / tile_size + 1, max_y / tile_size + 1, 3);
-    uint32_t md = 0;
-    for (uint32_t d : r.dist) md = std::max(md, d);
     for (uint32_t by = 0; by < r.bh; by++)
         for (uint32_t bx = 0; bx < r.bw; bx++) {
+            if (r.item[(size_t)by * r.bw + bx] == 0) continue;
             const double nd = md > 0 ? (double)r.dist[(size_t)by * r.bw + bx] / (double)md : 0.0;
             const uint8_t v = (uint8_t)(nd * 255.0);
             uint8_t *p = img.pixel(bx * dim / tile_size, by * dim / tile_size);  // stats.rs:176-191 (source coords / tile_size)

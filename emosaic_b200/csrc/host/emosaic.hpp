@@ -46,19 +46,26 @@ struct Image {
     bool operator==(const Image &o) const { return width == o.width && height == o.height && channels == o.channels && data == o.data; }
 };
 
-class Context {  // one per GPU
+// One GPU (emo_ctx), or several driven from this process (emo_group: library replicated by one NCCL broadcast, block rows
+// of the source / tiles of the library split into contiguous ranges — the reference's rayon tasks, rendering.rs:68-89 and
+// main.rs:760-794 — every GPU copying its stripe of the result straight into the caller's image).
+class Context {
 public:
     explicit Context(int device = 0);
+    explicit Context(const std::vector<int> &devices);  // devices.size() > 1: a group; analyse_tiles / render_nto1 shard over it
     ~Context();
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
-    emo_ctx *handle() const { return h_; }
+    emo_ctx *handle() const { return h_; }      // the (first) GPU: every single-GPU call runs here
+    emo_group *group() const { return g_; }     // nullptr for a single GPU
+    int gpus() const { return g_ ? emo_group_size(g_) : 1; }
     // 1to1 search index (include/emosaic_cuda.h §2b): built on demand by the match; these force or forbid it
     void build_index() const;
     void set_match_mode(int mode) const;  // EMO_MATCH_AUTO | EMO_MATCH_SCAN | EMO_MATCH_INDEX
 
 private:
     emo_ctx *h_ = nullptr;
+    emo_group *g_ = nullptr;
 };
 
 void check(int rc);  // throws Error(rc, emo_last_error()) when rc != 0

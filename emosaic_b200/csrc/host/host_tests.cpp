@@ -137,6 +137,47 @@ int main(int argc, char **argv) {
         Image im = render_stats(r, 1, 1);
         CHECK(im.width == 3 && im.height == 2 && im.pixel(0, 0)[0] == 141 && im.pixel(1, 0)[0] == 255 && im.pixel(2, 1)[0] == 28);
     });
+    // the reference's own stats tests, stats.rs:247-317 (empty summary, the two panics, test_render_basic), and unplaced blocks
+    run("test_stats_reference_cases", [] {
+        TileSet ts(1);
+        for (const char *p : {"test1.jpg", "test2.jpg"}) ts.push_tile(p, {255, 0, 0});
+        RenderResult empty;
+        CHECK(summarise(empty, ts, false).total == 0);                                       // test_summarise_empty: no panic
+        CHECK(throws_with([&] { render_stats(empty, 1, 16); }, "Cannot render visualization: no tiles recorded"));
+        RenderResult one;
+        one.bw = one.bh = 1; one.item = {1}; one.dist = {100};
+        CHECK(throws_with([&] { render_stats(one, 1, 0); }, "Tile size must be greater than 0"));
+        RenderResult r;  // test_summarise_with_tiles: tiles at (0,0) d=10, (10,10) d=20, (20,20) d=15; tile 1 used twice
+        r.bw = 3; r.bh = 1; r.item = {1, 2, 1}; r.dist = {10, 20, 15};
+        StatsSummary s = summarise(r, ts, false);
+        CHECK(s.total == 3 && s.unique == 2 && s.average_distance == 15.0 && s.top[0].first == "test1.jpg" && s.top[0].second == 2);
+        CHECK(s.worst[0].first == "test2.jpg" && s.worst[0].second == 20 && s.worst[2].second == 10);
+        RenderResult d;  // test_render_basic: (0,0) d=50 and (16,16) d=150 at tile size 16 -> 2x2, darker where the match is better
+        d.bw = d.bh = 2; d.item = {1, 0, 0, 1}; d.dist = {50, 0, 0, 150};
+        Image im = render_stats(d, 16, 16);
+        CHECK(im.width == 2 && im.height == 2 && im.pixel(0, 0)[0] < im.pixel(1, 1)[0] && im.pixel(1, 1)[0] == 255 && im.pixel(0, 0)[0] == 85);
+        // a no-repeat render that ran out of tiles (item 0, rendering.rs:347-351): not counted, no out_of_range
+        RenderResult u;
+        u.bw = 3; u.bh = 1; u.item = {2, 0, -1}; u.dist = {4, 999, 6};
+        StatsSummary su = summarise(u, ts, false);
+        CHECK(su.total == 2 && su.unique == 2 && su.average_distance == 5.0 && su.worst[0].second == 6);
+        CHECK(render_stats(u, 8, 8).width == 3 && render_stats(u, 8, 8).pixel(1, 0)[0] == 0);
+    });
+    // corrupt cache files fail with an Error before any out-of-bounds read or huge allocation (bincode Err -> re-analysis)
+    run("test_cache_corrupt_lengths", [] {
+        TileSet ts(1);
+        ts.push_tile("/tmp/a.jpg", {1, 2, 3}, std::optional<std::string>("2020:01:01"));
+        std::vector<uint8_t> blob = serialize_tile_set(ts);
+        std::vector<uint8_t> huge_T = blob;
+        for (int i = 0; i < 8; i++) huge_T[i] = 0xFF;
+        CHECK(throws_with([&] { deserialize_tile_set(huge_T, 1); }, "truncated"));
+        std::vector<uint8_t> huge_date = blob;  // date length field: 8 (T) + 8 (len) + 3 + 2 (idx) + 1 (tag) = offset 22
+        for (int i = 0; i < 8; i++) huge_date[22 + i] = 0xFF;
+        CHECK(throws_with([&] { deserialize_tile_set(huge_date, 1); }, "truncated"));
+        std::vector<uint8_t> huge_path = blob;
+        for (int i = 0; i < 8; i++) huge_path[blob.size() - 10 - 8 + i] = 0xFF;  // "/tmp/a.jpg" = 10 bytes, its length right before
+        CHECK(throws_with([&] { deserialize_tile_set(huge_path, 1); }, "truncated"));
+    });
     // PNG/PPM codec used by the CLI
     run("test_image_io_roundtrip", [] {
         Image im(5, 3, 3);

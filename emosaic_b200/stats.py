@@ -11,6 +11,59 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 
+class RenderStats:
+    """``RenderStats<D>`` (stats.rs:30-195) with the reference's interface: a map from the coordinates a tile was placed at
+    to (tile id, distance); ``push_tile`` on the same coordinates replaces the entry, like ``HashMap::insert``.  The renderers
+    fill it from the GPU's maps with ``from_maps`` instead of one ``push_tile`` per block under a mutex (rendering.rs:211-214)."""
+
+    def __init__(self):
+        self.tiles = {}          # (x, y) -> (signed 1-based tile id, distance); insertion-ordered
+
+    @classmethod
+    def from_maps(cls, item: np.ndarray, dist: np.ndarray, step: int) -> "RenderStats":
+        """Blocks of an item / dist map as entries at (bx * step, by * step): step = dim for render_nto1 (source coordinates,
+        rendering.rs:211-214), step = tile_size for render_nto1_no_repeat (output coordinates, :352-365).  Unplaced blocks
+        (item 0) have no entry."""
+        s = cls()
+        bh, bw = item.shape
+        for by in range(bh):
+            for bx in range(bw):
+                if item[by, bx] != 0:
+                    s.tiles[(bx * step, by * step)] = (int(item[by, bx]), int(dist[by, bx]))
+        return s
+
+    def push_tile(self, x: int, y: int, tile_idx: int, distance: int):
+        """stats.rs:56-64."""
+        self.tiles[(int(x), int(y))] = (int(tile_idx), int(distance))
+
+    def tile_count(self) -> int:
+        return len(self.tiles)
+
+    def summarise(self, paths: Optional[Sequence[str]] = None, file=sys.stderr) -> dict:
+        """stats.rs:87-139."""
+        if not self.tiles:
+            print("No tiles recorded in statistics", file=file)
+            return {}
+        v = list(self.tiles.values())
+        return summarise(np.array([t for t, _ in v], np.int64), np.array([d for _, d in v], np.uint64), paths, file)
+
+    def render(self, tile_size: int) -> np.ndarray:
+        """stats.rs:154-195: one grey pixel per (x / tile_size, y / tile_size), brightness (d / max_d * 255) as u8 in f64.  Entries
+        that land on the same pixel overwrite each other in the order of the map (the reference: HashMap iteration order)."""
+        if not self.tiles:
+            raise ValueError("Cannot render visualization: no tiles recorded")
+        if tile_size == 0:
+            raise ValueError("Tile size must be greater than 0")
+        max_x = max(x for x, _ in self.tiles)
+        max_y = max(y for _, y in self.tiles)
+        md = float(max(d for _, d in self.tiles.values()))
+        img = np.zeros((max_y // tile_size + 1, max_x // tile_size + 1, 3), np.uint8)
+        for (x, y), (_, d) in self.tiles.items():
+            nd = d / md if md > 0.0 else 0.0
+            img[y // tile_size, x // tile_size] = int(nd * 255.0)
+        return img
+
+
 def summarise(item: np.ndarray, dist: np.ndarray, paths: Optional[Sequence[str]] = None, file=sys.stderr) -> dict:
     """stats.rs:87-139: totals, unique images, average distance, top-10 usage, worst-10 matches."""
     if item.size == 0:
@@ -40,23 +93,27 @@ def summarise(item: np.ndarray, dist: np.ndarray, paths: Optional[Sequence[str]]
     return out
 
 
-def render(dist: np.ndarray, dim: int, tile_size: int) -> np.ndarray:
-    """stats.rs:154-195: grey-scale quality map, brightness = (d / max_d * 255) as u8 in f64.
+def render(dist: np.ndarray, dim: int, tile_size: int, placed: Optional[np.ndarray] = None) -> np.ndarray:
+    """stats.rs:154-195 over a whole dist map (vectorised ``RenderStats.from_maps(item, dist, dim).render(tile_size)``):
+    grey-scale quality map, brightness = (d / max_d * 255) as u8 in f64.
 
-    The reference keys its map by SOURCE coordinates (x = bx*dim, y = by*dim, rendering.rs:211-214) and then
-    divides by tile_size, so with tile_size > dim several blocks land on one pixel and the survivor depends on
-    HashMap iteration order.  Here the last block in row-major order wins (deterministic)."""
-    if dist.size == 0:
+    `dim` is the distance between the recorded coordinates of neighbouring blocks: render_nto1 records SOURCE coordinates
+    (x = bx*dim, rendering.rs:211-214), so with tile_size > dim several blocks land on one pixel and the reference's
+    survivor depends on HashMap iteration order — here the last block in row-major order wins (deterministic);
+    render_nto1_no_repeat records OUTPUT coordinates (x = bx*tile_size, rendering.rs:352-365): pass dim = tile_size and the
+    image has one pixel per block.  `placed` (bool map) masks blocks without a tile (no entry in the reference's map)."""
+    if placed is None:
+        placed = np.ones(dist.shape, bool)
+    if dist.size == 0 or not placed.any():
         raise ValueError("Cannot render visualization: no tiles recorded")
     if tile_size == 0:
         raise ValueError("Tile size must be greater than 0")
     bh, bw = dist.shape
-    max_x, max_y = (bw - 1) * dim, (bh - 1) * dim
+    ys_p, xs_p = np.nonzero(placed)
+    max_x, max_y = int(xs_p.max()) * dim, int(ys_p.max()) * dim
     img = np.zeros((max_y // tile_size + 1, max_x // tile_size + 1, 3), np.uint8)
-    md = float(dist.max())
+    md = float(dist[placed].max())
     norm = dist.astype(np.float64) / md if md > 0 else np.zeros(dist.shape)
     b = (norm * 255.0).astype(np.uint8)
-    ys = (np.arange(bh) * dim) // tile_size
-    xs = (np.arange(bw) * dim) // tile_size
-    img[ys[:, None], xs[None, :]] = b[:, :, None]
+    img[(ys_p * dim) // tile_size, (xs_p * dim) // tile_size] = b[ys_p, xs_p][:, None]
     return img

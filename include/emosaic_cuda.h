@@ -11,8 +11,9 @@
  *  - plain C types only; every function returns 0 on success or a negative emo_status;
  *    the message of the last failure on the calling thread is emo_last_error().
  *    Nothing unwinds across the boundary (the reference's panics/exit(1) become codes).
- *  - one emo_ctx per GPU (one process per GPU under torchrun / one ctx per device in a
- *    single process); a ctx is driven by one host thread at a time.
+ *  - one emo_ctx per GPU; a ctx is driven by one host thread at a time.  Several GPUs are used either as one
+ *    process per GPU (emo_comm_init_rank joins the ctx to an NCCL communicator) or from one process through an
+ *    emo_group (one ctx per device, one worker thread per device inside the group calls); see "multi-GPU".
  *  - `*_dev` variants take DEVICE pointers (same CUDA primary context, e.g. memory from
  *    emo_dev_alloc or any CUDA allocator) and are asynchronous on the ctx stream;
  *    the un-suffixed variants take HOST pointers, stage through the ctx's own device
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 1
+#define EMO_ABI_VERSION 2
 
 typedef struct emo_ctx emo_ctx;
 
@@ -43,7 +44,8 @@ typedef enum emo_status {
     EMO_ERR_OOM = -3,         /* device or pinned-host allocation failed */
     EMO_ERR_STATE = -4,       /* call sequence error (e.g. match before set_library) */
     EMO_ERR_UNSUPPORTED = -5, /* valid in the reference but not implemented by this build */
-    EMO_ERR_NO_DEVICE = -6    /* no CUDA device / wrong architecture: there is no CPU path */
+    EMO_ERR_NO_DEVICE = -6,   /* no CUDA device / wrong architecture: there is no CPU path */
+    EMO_ERR_NCCL = -7         /* NCCL could not be loaded or a collective failed */
 } emo_status;
 
 int emo_abi_version(void);
@@ -127,6 +129,9 @@ int emo_analyse_fused_dev(emo_ctx *ctx, const uint8_t *tiles_dev, uint64_t T, ui
 int emo_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts);
 int emo_set_library_dev(emo_ctx *ctx, const uint8_t *colors_dev, const uint8_t *tile_px_dev, uint32_t T, uint32_t N,
                         uint32_t ts);
+/* Shape of the resident library (all 0 when none is set; ts == 0 without tile pixels) — what a rank that received its
+ * library from emo_comm_set_library needs to size its buffers.  Any output may be NULL. */
+int emo_library_info(emo_ctx *ctx, uint32_t *T, uint32_t *N, uint32_t *ts);
 
 /* ---- (2b) search index (1to1) ---------------------------------------------------------------
  * The GPU analogue of the KD-tree that TileSet::build_kiddo() (tiles/tileset.rs:178-190) returns and
@@ -210,13 +215,67 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
 int emo_mosaic_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, uint32_t out_channels,
                    uint8_t tint_alpha, int32_t *item_dev, uint32_t *dist_dev, uint8_t *out_dev);
 
-/* ---- measurement helpers ------------------------------------------------------------------
- * Integer-pipe microbenchmark used as the roofline denominator of the match kernel:
- * dependent-free streams of VABSDIFF4 / VIMNMX3 / IMAD on every SM.
- * which: 0 = scalar INT32 (IMAD), 1 = VABSDIFF4.ACC, 2 = VIMNMX3, 3 = the first match inner-loop mix,
- * 4 = HFMA2, 5 = HADD2, 6 = VABSDIFF4+HFMA2, 7 = VABSDIFF4+HADD2, 8 = VABSDIFF4+IMAD (dual-pipe probes)
- * (4 VABSDIFF4 + 2 VIMNMX3).  Returns thread-level instructions per second. */
-int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s);
+/* ---- multi-GPU -----------------------------------------------------------------------------------
+ * The path shards without an exchange step.  The units are the reference's own parallel tasks: one block row of
+ * the source per task in render() ((0..H).into_par_iter().step_by(step), src/mosaic/rendering.rs:68-89, strips
+ * merged at :91-99) and one tile per task in the analysis build (src/main.rs:760-794).  GPU r of n takes the
+ * contiguous range emo_stripe_bounds(units, n, r); every GPU holds the whole library, replicated once by an NCCL
+ * broadcast over NVLink; stripes of the output are disjoint row ranges of ONE host image, and each GPU copies its
+ * stripe straight to its row offset — that copy is the host-side concatenation, there is no second one.
+ * No collective runs inside the match / compose loop.
+ *
+ * NCCL is loaded at run time (dlopen: $EMO_NCCL_LIB, else the libnccl.so.2 already in the process, else the
+ * system's) the first time a call needs it, so single-GPU hosts do not need NCCL installed; EMO_ERR_NCCL if absent. */
+
+/* [start, stop) of `units` for part `rank` of `world`: contiguous, sizes differ by at most one. */
+void emo_stripe_bounds(uint64_t units, int world, int rank, uint64_t *start, uint64_t *stop);
+
+/* Pinned host memory for images the multi-GPU calls copy to and from.  emo_host_register pins memory the caller
+ * already owns (e.g. a Rust Vec<u8> behind an RgbImage) for the duration of a render. */
+int emo_host_register(void *p, size_t bytes);
+int emo_host_unregister(void *p);
+
+/* (a) one process per GPU (torchrun, MPI, ...).  Rank 0 calls emo_comm_unique_id and hands the 128 bytes to every
+ * rank by any means (a file, torchrun's store, MPI_Bcast); every rank then calls emo_comm_init_rank on its ctx
+ * (collective: ncclCommInitRank).  After that:
+ *   emo_comm_set_library[_dev]: emo_set_library on every rank from the root's data.  On the root the arguments are
+ *     those of emo_set_library[_dev]; on the other ranks colors / tile_px / T / N / ts are ignored (pass NULL / 0):
+ *     the root's sizes travel in a header, the colours and tile pixels in one ncclBroadcast each.
+ *   emo_comm_broadcast_dev: ncclBroadcast of a device buffer (e.g. the source image), in place.
+ *   emo_comm_allgather_analysis_dev: the sharded analysis build — rank r analysed the tiles of
+ *     emo_stripe_bounds(T, world, r) into local_dev [(stop - start) * bytes_per_tile]; afterwards all_dev
+ *     [T * bytes_per_tile] holds every rank's results in tile order on every rank (one ncclAllGather).
+ * The *_dev collectives are asynchronous on the ctx stream like every *_dev call. */
+#define EMO_COMM_ID_BYTES 128
+int emo_comm_unique_id(void *id_out /* [EMO_COMM_ID_BYTES] */);
+int emo_comm_init_rank(emo_ctx *ctx, const void *id, int rank, int world);
+int emo_comm_info(emo_ctx *ctx, int *rank, int *world, int *nccl_version);
+int emo_comm_set_library(emo_ctx *ctx, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts,
+                         int root);
+int emo_comm_set_library_dev(emo_ctx *ctx, const uint8_t *colors_dev, const uint8_t *tile_px_dev, uint32_t T, uint32_t N,
+                             uint32_t ts, int root);
+int emo_comm_broadcast_dev(emo_ctx *ctx, void *buf_dev, size_t bytes, int root);
+int emo_comm_allgather_analysis_dev(emo_ctx *ctx, const uint8_t *local_dev, uint64_t T, uint32_t bytes_per_tile,
+                                    uint8_t *all_dev);
+
+/* (b) one process, several GPUs: an emo_group owns one ctx per device and (for n > 1) their communicators
+ * (ncclCommInitAll).  Group calls take HOST pointers, are synchronous on return and run one worker thread per GPU.
+ *   emo_group_set_library: H2D on the first device, ncclBroadcast to the others, search set built on every GPU.
+ *   emo_group_analyse[_fused]: tiles sharded by emo_stripe_bounds(T, n, r); every GPU writes its range of `out`.
+ *   emo_group_mosaic: block rows sharded by emo_stripe_bounds(H / dim, n, r); GPU r uploads its source stripe,
+ *     matches, composes and copies its output stripe (and its rows of item / dist, which may be NULL) to its row
+ *     offset in `out`.  Results are bit-identical to emo_mosaic on one GPU.
+ * emo_group_ctx gives access to one member for the single-GPU calls (e.g. emo_set_match_mode, emo_launch_count). */
+typedef struct emo_group emo_group;
+int emo_group_create(const int *devices, int n, emo_group **out); /* devices == NULL: ordinals 0..n-1 */
+void emo_group_destroy(emo_group *g);
+int emo_group_size(const emo_group *g);
+emo_ctx *emo_group_ctx(emo_group *g, int i);
+int emo_group_set_library(emo_group *g, const uint8_t *colors, const uint8_t *tile_px, uint32_t T, uint32_t N, uint32_t ts);
+int emo_group_analyse(emo_group *g, const uint8_t *tiles, uint64_t T, uint32_t ts, uint32_t dim, uint8_t *out);
+int emo_group_analyse_fused(emo_group *g, const uint8_t *tiles, uint64_t T, uint32_t ts, uint8_t *out1, uint8_t *out4);
+int emo_group_mosaic(emo_group *g, const uint8_t *src, uint32_t W, uint32_t H, uint32_t out_channels, uint8_t tint_alpha,
+                     int32_t *item, uint32_t *dist, uint8_t *out);
 
 #ifdef __cplusplus
 }

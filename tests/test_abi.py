@@ -29,7 +29,7 @@ def test_header_symbols_exported():
 def test_abi_version_and_error_string():
     from emosaic_b200 import _lib
     lib = _lib.load()
-    assert lib.emo_abi_version() == 1
+    assert lib.emo_abi_version() == 2
     assert isinstance(lib.emo_last_error(), bytes)
 
 
@@ -79,3 +79,45 @@ def test_resize_null_and_argument_checks_need_no_gpu():
     lib = _lib.load()
     assert lib.emo_resize(None, None, 1, 4, 4, 0, 0, 4, 4, 2, 2, None) == -1
     assert b"ctx is NULL" in lib.emo_last_error()
+
+
+def test_stripe_bounds_matches_python_sharding():
+    """emo_stripe_bounds (the C ABI's partition of block rows / tiles over GPUs) == sharding.stripe_bounds, and the parts tile the range."""
+    import emosaic_b200 as emo
+    from emosaic_b200 import sharding
+    for units in (0, 1, 7, 37, 4096, 1_000_003):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                a, b = emo.stripe_bounds(units, world, r)
+                assert (a, b) == sharding.stripe_bounds(units, world, r)
+                assert a == prev and b >= a
+                prev = b
+            assert prev == units
+    assert emo.stripe_bounds(10, 2, 5) == (0, 0)        # rank outside the world: empty range, no crash
+
+
+def test_group_and_comm_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import emosaic_b200 as emo
+    with pytest.raises(emo.EmosaicError) as e:
+        emo.Group(2)
+    assert e.value.code == -6
+    from emosaic_b200 import _lib
+    lib = _lib.load()
+    assert lib.emo_group_mosaic(None, None, 4, 4, 3, 0, None, None, None) == -1
+    assert lib.emo_comm_init_rank(None, None, 0, 1) == -1
+    assert lib.emo_group_size(None) == 0 and lib.emo_group_ctx(None, 0) is None
+
+
+def test_probe_library_is_separate():
+    """Measurement code is not part of the product ABI: emo_probe_* live in tools/libemosaic_probe.so only."""
+    from emosaic_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    assert not hasattr(lib, "emo_probe_int_pipe")
+    from tools import probe
+    if os.path.exists(probe.LIB_PATH):
+        p = ctypes.CDLL(probe.LIB_PATH)
+        assert hasattr(p, "emo_probe_int_pipe") and hasattr(p, "emo_probe_host_copy")

@@ -152,3 +152,39 @@ def test_cli_prepare_subcommand(workdir):
         out = d / f"prepared_{int(crop)}.png"
         assert cli.main(["-s", "12", "-o", str(out)] + (["--crop"] if crop else []) + [photo, "prepare"]) == 0
         assert (np.asarray(PIL.open(out)) == oracle_tile(photo, 12, crop)).all()
+
+
+def test_cli_skips_unreadable_and_undersized_tiles(workdir, capsys):
+    """generate_tile_set (main.rs:757-806): a corrupt file and a photo smaller than the tile size are listed under
+    'Failed to read the following images(n)' and left out; the survivors are numbered 1..n in walk order; the no-repeat
+    statistics image has one pixel per block (output coordinates, rendering.rs:352-365)."""
+    d, src = workdir
+    bad = d / "tiles_bad"
+    bad.mkdir()
+    rng = np.random.default_rng(5)
+    good = []
+    for i in range(30):
+        img = np.clip(rng.integers(0, 226, 3) + rng.integers(-20, 21, (30, 30, 3)), 0, 225).astype(np.uint8)
+        PIL.fromarray(img).save(bad / f"g{i:02d}.jpg", quality=95)
+        good.append(str(bad / f"g{i:02d}.jpg"))
+    (bad / "broken.jpg").write_bytes(b"\xff\xd8\xff\xe0 this is not a jpeg")
+    PIL.fromarray(rng.integers(0, 200, (5, 40, 3), dtype=np.uint8)).save(bad / "tiny.jpg")      # 5 rows < tile size 8
+    small = src[:4, :6]
+    PIL.fromarray(small).save(d / "small_bad.png")
+    out = d / "out_bad.png"
+    assert cli.main(["-s", "8", "-o", str(out), str(d / "small_bad.png"), "mosaic", str(bad), "-f", "--no-repeat"]) == 0
+    err = capsys.readouterr().err
+    assert "Failed to read the following images(2):" in err and "- broken.jpg" in err and "- tiny.jpg" in err
+    assert "Tile set with 30 tiles" in err
+    from oracle import oracle_np as onp
+    px = np.stack([oracle_tile(p, 8, False) for p in sorted(good)])
+    px_rd = np.stack([oracle_tile(p, 8, True) for p in sorted(good)])
+    colors = oracle.analyse_tiles(px, 1)
+    item, dist = onp.no_repeat_assign(colors, small)
+    assert (np.asarray(PIL.open(out)) == oracle.render(px_rd, item)).all()
+    stats_img = np.asarray(PIL.open(str(out)[:-4] + ".stats.png"))
+    assert stats_img.shape[:2] == (4, 6)                                  # one pixel per block
+    md = float(dist.max())
+    assert (stats_img[..., 0] == (dist / md * 255.0).astype(np.uint8)).all()
+    paths = cache.deserialize_tile_set((bad / ".emosaic_1to1").read_bytes(), 1)[1]
+    assert [os.path.basename(p) for p in paths] == [f"g{i:02d}.jpg" for i in range(30)]

@@ -7,7 +7,8 @@ import emosaic_b200 as emo
 
 ctx = emo.Context(0)
 dev = torch.device("cuda", 0)
-peak = ctx.probe_int_pipe(1)  # VABSDIFF4 thread-instr/s
+from tools.probe import probe_int_pipe
+peak = probe_int_pipe(0, 1)  # VABSDIFF4 thread-instr/s
 for N, T, S in ((4, 20000, 2048), (9, 20000, 2040), (16, 20000, 2048), (25, 20000, 2000), (64, 10000, 2048), (256, 5000, 2048), (1024, 4000, 2048), (16384, 2000, 2048)):
     dim = int(N ** 0.5)
     colors = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (T * N * 3,), dtype=np.uint8)).to(dev)

@@ -1,7 +1,20 @@
 // probe.cu — integer-pipe microbenchmark: the roofline denominator of the match kernel.
 // Every SM runs resident warps issuing independent chains of one instruction class; the result is
 // thread-level instructions per second (warp instructions x 32), measured with CUDA events.
-#include "common.cuh"
+// Measurement code: built as tools/libemosaic_probe.so, NOT part of libemosaic_cuda.so or its public header.
+//   int emo_probe_int_pipe(int device, int which, double *inst_per_s)
+//   which: 0 = scalar INT32 (IMAD), 1 = VABSDIFF4.ACC, 2 = VIMNMX3, 3 = the first match inner-loop mix (4 VABSDIFF4 +
+//   2 VIMNMX3), 4 = HFMA2, 5 = HADD2, 6 = VABSDIFF4+HFMA2, 7 = VABSDIFF4+HADD2, 8 = VABSDIFF4+IMAD, 9 = HMNMX2,
+//   10 = VABSDIFF4+HMNMX2 (dual-pipe probes).  Returns 0 or a negative cudaError.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;  // SASS: VABSDIFF4.U8.ACC
+}
+#define PROBE_CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return -(int)e__; } while (0)
 
 template <int WHICH>
 __global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed, int iters) {
@@ -59,39 +72,45 @@ __global__ void __launch_bounds__(256) probe_kernel(uint32_t *out, uint32_t seed
     if (r == 0x12345678u) out[0] = r;  // keep the chains alive
 }
 
-extern "C" int emo_probe_int_pipe(emo_ctx *ctx, int which, double *inst_per_s) {
-    EMO_REQUIRE(ctx && inst_per_s, EMO_ERR_ARG, "emo_probe_int_pipe: NULL argument");
-    EMO_REQUIRE(which >= 0 && which <= 10, EMO_ERR_ARG, "emo_probe_int_pipe: which must be 0..10");
-    EMO_CK(cudaSetDevice(ctx->device));
-    int rc = emo_ensure(ctx, &ctx->stage[1], &ctx->stage_cap[1], 256);
-    if (rc) return rc;
-    uint32_t *out = (uint32_t *)ctx->stage[1];
-    const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
+extern "C" int emo_probe_int_pipe(int device, int which, double *inst_per_s) {
+    if (!inst_per_s || which < 0 || which > 10) return -(int)cudaErrorInvalidValue;
+    PROBE_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PROBE_CK(cudaGetDeviceProperties(&prop, device));
+    uint32_t *out = nullptr;
+    PROBE_CK(cudaMalloc(&out, 256));
+    cudaEvent_t e0, e1;
+    PROBE_CK(cudaEventCreate(&e0));
+    PROBE_CK(cudaEventCreate(&e1));
+    const int iters = 4096, grid = prop.multiProcessorCount * 8, block = 256;
     // thread-level instructions per iteration of the measured class(es)
     const double per_iter = which == 3 ? 4.0 * 8 * 6 : ((which == 2 || which >= 6) ? 4.0 * 8 * 2 : 4.0 * 8);
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
-        EMO_CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+        PROBE_CK(cudaEventRecord(e0, 0));
         switch (which) {
-            case 0: probe_kernel<0><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 1: probe_kernel<1><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 2: probe_kernel<2><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 3: probe_kernel<3><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 4: probe_kernel<4><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 5: probe_kernel<5><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 6: probe_kernel<6><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 7: probe_kernel<7><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 8: probe_kernel<8><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            case 9: probe_kernel<9><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
-            default: probe_kernel<10><<<grid, block, 0, ctx->stream>>>(out, 12345u + rep, iters); break;
+            case 0: probe_kernel<0><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 1: probe_kernel<1><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 2: probe_kernel<2><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 3: probe_kernel<3><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 4: probe_kernel<4><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 5: probe_kernel<5><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 6: probe_kernel<6><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 7: probe_kernel<7><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 8: probe_kernel<8><<<grid, block>>>(out, 12345u + rep, iters); break;
+            case 9: probe_kernel<9><<<grid, block>>>(out, 12345u + rep, iters); break;
+            default: probe_kernel<10><<<grid, block>>>(out, 12345u + rep, iters); break;
         }
-        EMO_LAUNCH_CHECK(ctx);
-        EMO_CK(cudaEventRecord(ctx->ev_stop, ctx->stream));
-        EMO_CK(cudaEventSynchronize(ctx->ev_stop));
+        PROBE_CK(cudaGetLastError());
+        PROBE_CK(cudaEventRecord(e1, 0));
+        PROBE_CK(cudaEventSynchronize(e1));
         float ms = 0;
-        EMO_CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        PROBE_CK(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best) best = ms;
     }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
     *inst_per_s = per_iter * iters * (double)grid * block / (best * 1e-3);
-    return EMO_OK;
+    return 0;
 }
