@@ -41,8 +41,9 @@ def _isqrt_exact(N: int) -> int:
     return d
 
 
-MATCH_AUTO, MATCH_SCAN, MATCH_INDEX = 0, 1, 2
-MATCH_MODES = {"auto": MATCH_AUTO, "scan": MATCH_SCAN, "index": MATCH_INDEX}
+MATCH_AUTO, MATCH_SCAN, MATCH_INDEX, MATCH_INDEX_WIDE, MATCH_INDEX_COMPACT = 0, 1, 2, 3, 4
+MATCH_MODES = {"auto": MATCH_AUTO, "scan": MATCH_SCAN, "index": MATCH_INDEX, "index_wide": MATCH_INDEX_WIDE,
+               "index_compact": MATCH_INDEX_COMPACT}
 
 
 class Context:
@@ -259,7 +260,8 @@ class Context:
         check(self._lib.emo_build_index(self._h))
 
     def set_match_mode(self, mode: int | str):
-        """'auto' (default) | 'scan' (brute force) | 'index' (colour-cube table when the library supports one)."""
+        """'auto' (default) | 'scan' (brute force) | 'index' (colour-cube table when the library supports one) |
+        'index_wide' / 'index_compact' (the index with its 64 MiB / 32 MiB form forced)."""
         if isinstance(mode, str):
             mode = MATCH_MODES[mode]
         check(self._lib.emo_set_match_mode(self._h, int(mode)))

@@ -84,6 +84,12 @@ struct emo_ctx {
     bool has_px = false;
     uint32_t *lut = nullptr;  // 1to1 search index: [256 b][256 g][256 r] keys dist << 22 | tile (index.cu), 64 MiB
     bool lut_valid = false;   // built for the resident library
+    uint16_t *lut16 = nullptr;  // compact form: slot of the winner per cell, 32 MiB (index.cu)
+    int lut16_mode = 0;         // 0: none, 1: slot = tile index (T <= 65 536), 2: slot -> idx_entry {tile, colour}
+    uint32_t lut16_slots = 0;
+    uint32_t *idx_slot_of_tile = nullptr;  // build scratch of mode 2
+    size_t idx_slot_cap = 0;
+    uint2 *idx_entry = nullptr;            // [65 536] {tile, colour} + the winner counter
     int match_mode = 0;       // EMO_MATCH_AUTO / SCAN / INDEX
 
     // scratch
@@ -230,6 +236,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 __device__ __forceinline__ uint32_t ldg_nc_hint_u32(const void *p, uint64_t pol) {
     uint32_t r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_nc_hint_u16(const void *p, uint64_t pol) {
+    uint16_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ void stg_hint_v4(void *p, uint4 v, uint64_t pol) {

@@ -74,6 +74,9 @@ void emo_destroy(emo_ctx *ctx) {
     cudaFree(ctx->cand);
     cudaFree(ctx->lib_px);
     cudaFree(ctx->lut);
+    cudaFree(ctx->lut16);
+    cudaFree(ctx->idx_slot_of_tile);
+    cudaFree(ctx->idx_entry);
     cudaFree(ctx->keys);
     cudaFree(ctx->qvec);
     cudaFree(ctx->err_flag);
@@ -414,6 +417,7 @@ int emo_library_common(emo_ctx *ctx, uint32_t T, uint32_t N, uint32_t ts, bool h
     }
     ctx->T = T; ctx->N = N; ctx->dim = dim; ctx->ts = ts; ctx->words = words;
     ctx->lut_valid = false;  // the search index belongs to the previous library
+    ctx->lut16_mode = 0;
     ctx->L = (N == 1) ? T : 2 * T;  // for N == 1 a tile and its mirror coincide; the mirror can never win a tie
     uint32_t chunk = (words == 1) ? 1024 : (words == 3 ? 512 : 256);
     if (ctx->wide) chunk = 128;  // candidate tile of match_wide_kernel
@@ -481,7 +485,7 @@ int emo_build_index(emo_ctx *ctx) {
 
 int emo_set_match_mode(emo_ctx *ctx, int mode) {
     EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_set_match_mode: ctx is NULL");
-    EMO_REQUIRE(mode == EMO_MATCH_AUTO || mode == EMO_MATCH_SCAN || mode == EMO_MATCH_INDEX, EMO_ERR_ARG,
+    EMO_REQUIRE(mode >= EMO_MATCH_AUTO && mode <= EMO_MATCH_INDEX_COMPACT, EMO_ERR_ARG,
                 "emo_set_match_mode: unknown mode %d", mode);
     ctx->match_mode = mode;
     return EMO_OK;

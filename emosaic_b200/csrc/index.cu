@@ -17,9 +17,17 @@
 // the scan kernel.
 //
 // Layout in HBM: lut[b][g][r] u32 (cell = r | g << 8 | b << 16, i.e. the low 24 bits of the pixel
-// read as a little-endian word), 64 MiB, resident in the 126 MB L2 while the source streams through.
-// Cost: build = 1 memset + 4 small kernels (about 0.1 ms, once per library); lookup = 3 B read +
-// 8 B written per query plus one L2-resident gather.
+// read as a little-endian word), 64 MiB.  Cost: build = 1 memset + 4 small kernels (about 0.1 ms, once per
+// library); lookup = 3 B read + 8 B written per query plus one gather.
+//
+// Compact form (lut16, 32 MiB): the 64 MiB table is more than the ~63 MB of L2 that one die of the B200 keeps of
+// a table every SM reads, so next to a streaming output it is re-fetched from DRAM on every pass.  A cell only has
+// to name its winner: lut16[cell] = slot (u16), and the distance is recomputed from the winner's colour
+// (one VABSDIFF4).  slot = tile index when T <= 65 536 — every library the reference can load (i16 ids,
+// tileset.rs:182) — and then the colours are the candidate array itself, staged in shared memory when they fit
+// (T <= 57 344: the second lookup costs no L1 wavefront); larger libraries are compacted to their distinct winners
+// (tiles with duplicate colours never win: C4's 100 000 tiles have 43 909 distinct colours) with an
+// 8-byte {tile, colour} entry per slot, used where the launch is small enough that the cold table dominates.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -117,6 +125,42 @@ __global__ void __launch_bounds__(256) index_sweep_kernel(uint32_t *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// compact form: u16 slot per cell
+// ---------------------------------------------------------------------------------------
+static constexpr uint32_t IDX16_SLOTS = 65536;
+static constexpr uint32_t IDX16_SMEM_SLOTS = 57344;  // 224 KB of colours: the most a CTA's shared memory holds
+
+// winners = tiles that own their own colour cell (dist 0, smallest index among duplicates); slots in arrival order
+// (which slot a winner gets does not matter: results depend only on the slot -> {tile, colour} pairing)
+__global__ void index_winners_kernel(const uint32_t *__restrict__ cand, uint32_t T, const uint32_t *__restrict__ lut,
+                                     uint32_t *__restrict__ slot_of_tile, uint2 *__restrict__ entry, uint32_t *__restrict__ counter) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const uint32_t c = cand[t] & 0xFFFFFFu;
+    if ((lut[c] & IDX_TILE_MASK) != t) return;
+    const uint32_t s = atomicAdd(counter, 1u);
+    if (s < IDX16_SLOTS) {
+        slot_of_tile[t] = s;
+        entry[s] = make_uint2(t, c);
+    }
+}
+
+// lut16[cell] = slot of the cell's winner; 8 cells per thread.  DIRECT: slot = tile index.
+template <bool DIRECT>
+__global__ void __launch_bounds__(256) index_compact_kernel(const uint32_t *__restrict__ lut, const uint32_t *__restrict__ slot_of_tile,
+                                                            uint16_t *__restrict__ lut16) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const uint4 a = *reinterpret_cast<const uint4 *>(lut + i), b = *reinterpret_cast<const uint4 *>(lut + i + 4);
+    uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        k[m] &= IDX_TILE_MASK;
+        if (!DIRECT) k[m] = __ldg(slot_of_tile + k[m]);
+    }
+    *reinterpret_cast<uint4 *>(lut16 + i) = make_uint4(k[0] | k[1] << 16, k[2] | k[3] << 16, k[4] | k[5] << 16, k[6] | k[7] << 16);
+}
+
 int emo_launch_build_index(emo_ctx *ctx) {
     if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
     EMO_CK(cudaMemsetAsync(ctx->lut, 0xFF, IDX_CELLS * sizeof(uint32_t), ctx->stream));
@@ -129,6 +173,35 @@ int emo_launch_build_index(emo_ctx *ctx) {
     index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
     EMO_LAUNCH_CHECK(ctx);
     ctx->lut_valid = true;
+    // the compact form
+    ctx->lut16_mode = 0;
+    static const bool wide_only = getenv("EMO_INDEX_WIDE") && atoi(getenv("EMO_INDEX_WIDE")) != 0;  // tests / tuning: u32 table only
+    if (wide_only) return EMO_OK;
+    if (!ctx->lut16) EMO_CK(cudaMalloc(&ctx->lut16, IDX_CELLS * sizeof(uint16_t)));
+    if (ctx->T <= IDX16_SLOTS) {
+        index_compact_kernel<true><<<(uint32_t)(IDX_CELLS / 8 / 256), 256, 0, ctx->stream>>>(ctx->lut, nullptr, ctx->lut16);
+        EMO_LAUNCH_CHECK(ctx);
+        ctx->lut16_slots = ctx->T;
+        ctx->lut16_mode = 1;  // slot = tile index, colours = the candidate array
+        return EMO_OK;
+    }
+    // larger libraries: distinct winners, if there are at most 65 536 of them
+    int rc;
+    if ((rc = emo_ensure(ctx, (void **)&ctx->idx_slot_of_tile, &ctx->idx_slot_cap, (size_t)ctx->T * 4))) return rc;
+    if (!ctx->idx_entry) EMO_CK(cudaMalloc(&ctx->idx_entry, IDX16_SLOTS * sizeof(uint2) + 16));
+    uint32_t *counter = reinterpret_cast<uint32_t *>(ctx->idx_entry + IDX16_SLOTS);
+    EMO_CK(cudaMemsetAsync(counter, 0, 4, ctx->stream));
+    index_winners_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->lut, ctx->idx_slot_of_tile, ctx->idx_entry,
+                                                                        counter);
+    EMO_LAUNCH_CHECK(ctx);
+    uint32_t winners = 0;
+    EMO_CK(cudaMemcpyAsync(&winners, counter, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaStreamSynchronize(ctx->stream));  // once per library: the slot count decides which lookup kernels may run
+    if (winners > IDX16_SLOTS) return EMO_OK;    // too many distinct colours: the 64 MiB table serves every lookup
+    index_compact_kernel<false><<<(uint32_t)(IDX_CELLS / 8 / 256), 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_slot_of_tile, ctx->lut16);
+    EMO_LAUNCH_CHECK(ctx);
+    ctx->lut16_slots = winners;
+    ctx->lut16_mode = 2;  // slot -> {tile, colour} entries
     return EMO_OK;
 }
 
@@ -187,8 +260,77 @@ __global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restr
     }
 }
 
-int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
-    const uint32_t Q = W * H;  // dim == 1: the source is a flat run of Q pixels
+// Lookup through the compact table: 4 pixels per thread, one u16 gather each, then the winner's colour
+//   MODE 0: slot = tile, colours staged in shared memory (one CTA per SM, filled once per launch)
+//   MODE 1: slot = tile, colours gathered from the candidate array (L1 / L2)
+//   MODE 2: slot -> {tile, colour} entries gathered from global memory (one 8-byte load)
+// and dist = |dr| + |dg| + |db| in one VABSDIFF4 (the fourth byte of both words is zero).
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 0 ? 1024 : 256)
+    match_index16_kernel(const uint8_t *__restrict__ src, const uint16_t *__restrict__ lut16, const uint32_t *__restrict__ colors,
+                         const uint2 *__restrict__ entry, uint32_t slots, uint32_t Q, int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
+    extern __shared__ uint32_t s_col[];
+    const uint32_t groups = Q >> 2;  // the launcher sends multiples of 4 pixels here and the tail to the wide kernel's scalar path
+    const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+    grid_dependency_wait();  // everything below may depend on the previous kernel of the stream (index build, item map readers)
+    if (MODE == 0) {
+        for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) s_col[i] = __ldg(colors + i) & 0xFFFFFFu;
+        __syncthreads();
+    }
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const uint32_t q0 = g << 2;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (size_t)g * 3;
+        const uint32_t w0 = ldg_nc_hint_u32(w, drop), w1 = ldg_nc_hint_u32(w + 1, drop), w2 = ldg_nc_hint_u32(w + 2, drop);
+        uint32_t c[4], sl[4], it[4], d[4];
+        c[0] = w0 & 0xFFFFFFu;
+        c[1] = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
+        c[2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
+        c[3] = w2 >> 8;
+#pragma unroll
+        for (int m = 0; m < 4; m++) sl[m] = ldg_nc_hint_u16(lut16 + c[m], keep);
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            uint32_t col;
+            if (MODE == 0) {
+                col = s_col[sl[m]];
+                it[m] = sl[m] + 1;
+            } else if (MODE == 1) {
+                col = __ldg(colors + sl[m]) & 0xFFFFFFu;
+                it[m] = sl[m] + 1;
+            } else {
+                const uint2 e = __ldg(entry + sl[m]);
+                col = e.y;
+                it[m] = e.x + 1;
+            }
+            d[m] = sad4(c[m], col, 0);
+        }
+        *reinterpret_cast<uint4 *>(item + q0) = make_uint4(it[0], it[1], it[2], it[3]);  // compose's input: kept in L2
+        stg_hint_v4(dist + q0, make_uint4(d[0], d[1], d[2], d[3]), drop);                // nothing on the device reads dist again
+    }
+}
+
+template <int MODE>
+static int launch_index16(emo_ctx *ctx, const uint8_t *src, uint32_t Q4, int32_t *item, uint32_t *dist) {
+    const uint32_t groups = Q4 >> 2;
+    if (MODE == 0) {
+        const size_t smem = (size_t)ctx->lut16_slots * 4;
+        // per device, and a group drives several from one process: set on every launch like the other kernels here
+        EMO_CK(cudaFuncSetAttribute(match_index16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDX16_SMEM_SLOTS * 4)));
+        // one resident CTA per SM when the colours take more than half of the shared memory, two otherwise
+        const uint32_t per_sm = smem > 110 * 1024 ? 1 : 2;
+        const uint32_t blocks = min((groups + 1023) / 1024, (uint32_t)ctx->sm_count * per_sm);
+        EMO_CK(emo_launch_pdl(match_index16_kernel<0>, dim3(blocks), dim3(1024), smem, ctx->stream, src, (const uint16_t *)ctx->lut16,
+                              (const uint32_t *)ctx->cand, (const uint2 *)nullptr, ctx->lut16_slots, Q4, item, dist));
+    } else {
+        const uint32_t blocks = min((groups + 255) / 256, (uint32_t)ctx->sm_count * 8 * 4);
+        EMO_CK(emo_launch_pdl(match_index16_kernel<MODE>, dim3(blocks), dim3(256), 0, ctx->stream, src, (const uint16_t *)ctx->lut16,
+                              (const uint32_t *)ctx->cand, (const uint2 *)ctx->idx_entry, ctx->lut16_slots, Q4, item, dist));
+    }
+    EMO_LAUNCH_CHECK(ctx);
+    return EMO_OK;
+}
+
+static int launch_index32(emo_ctx *ctx, const uint8_t *src, uint32_t Q, int32_t *item, uint32_t *dist) {
     const uint32_t groups = (Q + 3) >> 2;
     const uint32_t cap = (uint32_t)ctx->sm_count * 8 * 4;
     const uint32_t blocks = min((groups + 255) / 256, cap);
@@ -202,4 +344,29 @@ int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_
     else match_index_kernel<false, false><<<blocks, 256, 0, ctx->stream>>>(src, ctx->lut, Q, item, dist);
     EMO_LAUNCH_CHECK(ctx);
     return EMO_OK;
+}
+
+int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
+    const uint32_t Q = W * H;  // dim == 1: the source is a flat run of Q pixels
+    // which table: EMO_MATCH_INDEX_WIDE / EMO_MATCH_INDEX_COMPACT force one (tuning, tests); otherwise the compact table whenever its second
+    // lookup is free (colours in shared memory and enough pixels per SM to pay for staging them) or the launch is small
+    // enough that a cold 64 MiB table would dominate (a stripe of a multi-GPU run); the 64 MiB table for the rest.
+    const int forced = ctx->match_mode == EMO_MATCH_INDEX_WIDE ? 32 : ctx->match_mode == EMO_MATCH_INDEX_COMPACT ? 16 : 0;
+    const bool aligned = (uintptr_t)src % 4 == 0 && (uintptr_t)item % 16 == 0 && (uintptr_t)dist % 16 == 0;
+    int mode = -1;  // -1: the 64 MiB table
+    if (ctx->lut16_mode != 0 && aligned && Q >= 4 && forced != 32) {
+        const uint64_t per_sm = (uint64_t)Q / (uint64_t)ctx->sm_count;
+        if (ctx->lut16_mode == 1) {
+            if (ctx->lut16_slots <= IDX16_SMEM_SLOTS && (per_sm >= 2ull * ctx->lut16_slots || (forced == 16 && ctx->lut16_slots > 8192))) mode = 0;
+            else if (forced == 16 || Q <= (6u << 20) || ctx->lut16_slots <= 8192) mode = 1;
+        } else if (forced == 16 || Q <= (6u << 20)) {
+            mode = 2;
+        }
+    }
+    if (mode < 0) return launch_index32(ctx, src, Q, item, dist);
+    const uint32_t Q4 = Q & ~3u;
+    int rc = mode == 0 ? launch_index16<0>(ctx, src, Q4, item, dist) : mode == 1 ? launch_index16<1>(ctx, src, Q4, item, dist)
+                                                                               : launch_index16<2>(ctx, src, Q4, item, dist);
+    if (rc || Q4 == Q) return rc;
+    return launch_index32(ctx, src + (size_t)Q4 * 3, Q - Q4, item + Q4, dist + Q4);  // the last 1..3 pixels
 }

@@ -549,7 +549,7 @@ static int launch_match_wide(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint3
 // build plus the lookup cost about as much as scanning 2^31 (block, tile) pairs.  Same results either way.
 int emo_prepare_match(emo_ctx *ctx, uint64_t queries) {
     if (ctx->match_mode == EMO_MATCH_SCAN || ctx->lut_valid || !emo_index_supported(ctx)) return EMO_OK;
-    if (ctx->match_mode == EMO_MATCH_INDEX || queries * ctx->L >= (1ull << 31)) return emo_launch_build_index(ctx);
+    if (ctx->match_mode >= EMO_MATCH_INDEX || queries * ctx->L >= (1ull << 31)) return emo_launch_build_index(ctx);
     return EMO_OK;
 }
 

@@ -144,8 +144,13 @@ int emo_library_info(emo_ctx *ctx, uint32_t *T, uint32_t *N, uint32_t *ts);
  * emo_set_match_mode: EMO_MATCH_AUTO (default: use the index if it exists, build it on the first
  *   1to1 match whose scan would cost more than the build, i.e. blocks x tiles >= 2^31),
  *   EMO_MATCH_SCAN (always the brute-force scan kernel), EMO_MATCH_INDEX (always the index when the
- *   library supports one).  emo_set_library drops the index. */
-enum { EMO_MATCH_AUTO = 0, EMO_MATCH_SCAN = 1, EMO_MATCH_INDEX = 2 };
+ *   library supports one).  emo_set_library drops the index.
+ * The index has two forms with identical answers: the 64 MiB table (key = distance and tile per colour) and a compact
+ * 32 MiB one (u16 winner slot per colour, distance recomputed from the winner's colour) that stays L2-resident next to
+ * the output stream; the library picks per launch.  EMO_MATCH_INDEX_WIDE / EMO_MATCH_INDEX_COMPACT are EMO_MATCH_INDEX
+ * with that choice forced (tuning and tests; COMPACT falls back to WIDE for libraries with more than 65 536 distinct
+ * colours). */
+enum { EMO_MATCH_AUTO = 0, EMO_MATCH_SCAN = 1, EMO_MATCH_INDEX = 2, EMO_MATCH_INDEX_WIDE = 3, EMO_MATCH_INDEX_COMPACT = 4 };
 int emo_build_index(emo_ctx *ctx);
 int emo_set_match_mode(emo_ctx *ctx, int mode);
 

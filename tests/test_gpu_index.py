@@ -291,3 +291,74 @@ def test_index_random_sweep(ictx):
         if case % 3 == 0:
             ri, rd = oracle.match(colors, src)
             assert (ii == ri).all() and (id_ == rd).all(), f"case {case}"
+
+
+# ---- the compact form of the index (u16 winner slot per colour; index.cu) ------------------------------------------
+def _palette_library(T, P, seed):
+    """T tiles whose colours come from a palette of P distinct colours (duplicates: the smallest index must win)."""
+    rng = np.random.default_rng(seed)
+    pal = rng.choice(1 << 24, P, replace=False).astype(np.uint32)
+    pick = pal[rng.integers(0, P, T)]
+    return np.stack([pick & 255, (pick >> 8) & 255, pick >> 16], -1).astype(np.uint8).reshape(T, 1, 3)
+
+
+@pytest.mark.parametrize("T,P,H,W,why", [
+    (300, 0, 96, 128, "slot = tile, colours gathered from global (few pixels per SM)"),
+    (300, 0, 1024, 4096, "slot = tile, colours staged in shared memory"),
+    (40_000, 0, 64, 4096, "slot = tile, 160 KB of colours in shared memory (forced)"),
+    (60_000, 0, 128, 1024, "slot = tile, too many colours for shared memory"),
+    (65_536, 0, 64, 512, "largest library whose tile index fits a slot"),
+    (100_000, 40_000, 256, 4096, "more tiles than slots: compacted to the distinct winners"),
+    (70_000, 0, 64, 512, "more than 65 536 distinct colours: falls back to the 64 MiB table"),
+])
+def test_compact_index_equals_wide_index_and_scan(ictx, T, P, H, W, why):
+    colors = _palette_library(T, P, T) if P else np.random.default_rng(T).integers(0, 256, (T, 1, 3), dtype=np.uint8)
+    src = np.random.default_rng(T + 1).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    src[0, :4] = [[0, 0, 0], [255, 255, 255], colors[-1, 0], colors[0, 0]]
+    ictx.set_library(colors)
+    res = {}
+    for mode in ("index_wide", "index_compact", "auto"):
+        ictx.set_match_mode(mode)
+        res[mode] = ictx.match(src)
+    wi, wd = res["index_wide"]
+    for mode in ("index_compact", "auto"):
+        assert (res[mode][0] == wi).all() and (res[mode][1] == wd).all(), f"{mode} differs from the 64 MiB table: {why}"
+    rows = slice(0, min(H, 24))
+    ri, rd = oracle.KdTree(colors).match(src[rows])
+    assert (wi[rows] == ri).all() and (wd[rows] == rd).all()
+    # dist is the L1 distance to the chosen tile's colour everywhere
+    ch = colors[wi - 1, 0].astype(np.int64)
+    assert (np.abs(ch - src.astype(np.int64)).sum(-1) == wd).all()
+
+
+def test_compact_index_ragged_and_unaligned(ictx):
+    """Pixel counts that are not multiples of 4 (the tail goes through the scalar path) and device buffers at odd
+    addresses (the compact kernel needs aligned words: those launches take the 64 MiB table) give the same maps."""
+    import ctypes as C
+    colors = np.random.default_rng(3).integers(0, 256, (5000, 1, 3), dtype=np.uint8)
+    ictx.set_library(colors)
+    for H, W in ((1, 1), (1, 3), (3, 5), (7, 11), (31, 33)):
+        src = np.random.default_rng(H * W).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ictx.set_match_mode("index_compact")
+        ci, cd = ictx.match(src)
+        ictx.set_match_mode("scan")
+        si, sd = ictx.match(src)
+        assert (ci == si).all() and (cd == sd).all()
+    # unaligned device pointers through the *_dev call
+    H, W = 9, 13
+    src = np.random.default_rng(99).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ictx.set_match_mode("scan")
+    si, sd = ictx.match(src)
+    ictx.set_match_mode("index_compact")
+    Q = H * W
+    d_src = ictx.dev_alloc(Q * 3 + 64); d_item = ictx.dev_alloc(Q * 4 + 64); d_dist = ictx.dev_alloc(Q * 4 + 64)
+    try:
+        for so, io in ((1, 4), (0, 4), (3, 0), (0, 0)):
+            ictx.h2d(d_src + so, src)
+            ictx.match_dev(d_src + so, W, H, d_item + io, d_dist + io)
+            gi = np.zeros((H, W), np.int32); gd = np.zeros((H, W), np.uint32)
+            ictx.d2h(gi, d_item + io); ictx.d2h(gd, d_dist + io); ictx.sync()
+            assert (gi == si).all() and (gd == sd).all()
+    finally:
+        for p in (d_src, d_item, d_dist):
+            ictx.dev_free(p)

@@ -371,6 +371,27 @@ def test_config4_stripe_and_properties(ctx):
     assert (it == ri2).all()
 
 
+def test_config4_full_map(ctx):
+    """C4, the bench's headline workload, whole map: 4096 x 4096 source x 100 000 tiles.  item and dist of all 16.7 M blocks
+    against the KD-tree oracle (exact L1 nearest_one with the canonical tie-break; 1-2 minutes of host time), through the index
+    (both table forms) and through the brute-force scan."""
+    T = 100_000
+    tiles = np.random.default_rng(1234).integers(0, 256, (T, 8, 8, 3), dtype=np.uint8)
+    full = np.random.default_rng(5678).integers(0, 256, (4096, 4096, 3), dtype=np.uint8)
+    colors = ctx.analyse_tiles(tiles, 1)
+    assert (colors == oracle.analyse_tiles(tiles, 1)).all()
+    ctx.set_library(colors, tiles)
+    ri, rd = oracle.KdTree(colors).match(full)
+    try:
+        for mode in ("auto", "index_wide", "index_compact", "scan"):
+            ctx.set_match_mode(mode)
+            gi, gd = ctx.match(full)
+            assert (gi == ri).all(), f"{mode}: {(gi != ri).sum()} items differ from the oracle"
+            assert (gd == rd).all(), f"{mode}: {(gd != rd).sum()} distances differ from the oracle"
+    finally:
+        ctx.set_match_mode("auto")
+
+
 def test_config5_tint_large(ctx):
     """C5 geometry (ts 32, A=127, RGBA out) on a 128x256 source: oracle parity on the whole 4096x8192x4 image."""
     rng = np.random.default_rng(1234)

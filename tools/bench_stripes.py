@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import emosaic_b200 as emo
 
-T, ts, W, H = 100_000, 8, 4096, 4096
+T, ts, W, H = int(os.environ.get("T", "100000")), 8, 4096, 4096
+MODE = os.environ.get("MODE", "auto")   # auto | index_wide | index_compact
 ctx = emo.Context(0)
 dev = torch.device("cuda", 0)
 tiles = torch.from_numpy(np.random.default_rng(1234).integers(0, 256, (T * ts * ts * 3,), dtype=np.uint8)).to(dev)
@@ -17,6 +18,7 @@ out = torch.empty(H * ts * W * ts * 3, dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
 ctx.analyse_dev(tiles.data_ptr(), T, ts, 1, colors.data_ptr())
 ctx.set_library_dev(colors.data_ptr(), tiles.data_ptr(), T, 1, ts)
+ctx.set_match_mode(MODE)
 ctx.build_index(); ctx.sync()
 fused = os.environ.get("FUSED", "0") == "1"   # one emo_mosaic_dev call per step instead of match_dev + compose_dev
 base = None
@@ -42,5 +44,5 @@ for n in (1, 2, 4, 8):
     else:
         m = np.mean([ctx.mark_elapsed(3 * k, 3 * k + 1) for k in range(K)]); c = np.mean([ctx.mark_elapsed(3 * k + 1, 3 * k + 2) for k in range(K)])
     base = base or ms
-    print(f"hints={os.environ.get('EMO_L2_HINTS','0')} fused={int(fused)} rows={Hs:5d} (N={n}): step {ms*1e3:7.1f} us  match {m*1e3:6.1f} us  compose {c*1e3:6.1f} us  "
+    print(f"T={T} mode={MODE} fused={int(fused)} rows={Hs:5d} (N={n}): step {ms*1e3:7.1f} us  match {m*1e3:6.1f} us  compose {c*1e3:6.1f} us  "
           f"-> {H*W/n/ms/1e6:6.2f} G px/s per GPU, strong-scaling efficiency {base/(ms*n):.3f}")
