@@ -24,10 +24,9 @@
 // a table every SM reads, so next to a streaming output it is re-fetched from DRAM on every pass.  A cell only has
 // to name its winner: lut16[cell] = slot (u16), and the distance is recomputed from the winner's colour
 // (one VABSDIFF4).  slot = tile index when T <= 65 536 — every library the reference can load (i16 ids,
-// tileset.rs:182) — and then the colours are the candidate array itself, staged in shared memory when they fit
-// (T <= 57 344: the second lookup costs no L1 wavefront); larger libraries are compacted to their distinct winners
-// (tiles with duplicate colours never win: C4's 100 000 tiles have 43 909 distinct colours) with an
-// 8-byte {tile, colour} entry per slot, used where the launch is small enough that the cold table dominates.
+// tileset.rs:182) — and then the colours are the candidate array itself; larger libraries are compacted to their
+// distinct winners (tiles with duplicate colours never win: C4's 100 000 tiles have 43 909 distinct colours) with an
+// 8-byte {tile, colour} entry per slot.  The second lookup goes to an array of at most 512 KB (L1 / L2).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -129,7 +128,6 @@ __global__ void __launch_bounds__(256) index_sweep_kernel(uint32_t *__restrict__
 // compact form: u16 slot per cell
 // ---------------------------------------------------------------------------------------
 static constexpr uint32_t IDX16_SLOTS = 65536;
-static constexpr uint32_t IDX16_SMEM_SLOTS = 57344;  // 224 KB of colours: the most a CTA's shared memory holds
 
 // winners = tiles that own their own colour cell (dist 0, smallest index among duplicates); slots in arrival order
 // (which slot a winner gets does not matter: results depend only on the slot -> {tile, colour} pairing)
@@ -261,22 +259,18 @@ __global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restr
 }
 
 // Lookup through the compact table: 4 pixels per thread, one u16 gather each, then the winner's colour
-//   MODE 0: slot = tile, colours staged in shared memory (one CTA per SM, filled once per launch)
-//   MODE 1: slot = tile, colours gathered from the candidate array (L1 / L2)
-//   MODE 2: slot -> {tile, colour} entries gathered from global memory (one 8-byte load)
-// and dist = |dr| + |dg| + |db| in one VABSDIFF4 (the fourth byte of both words is zero).
+//   MODE 1: slot = tile, colours gathered from the candidate array
+//   MODE 2: slot -> {tile, colour} entries (one 8-byte load)
+// and dist = |dr| + |dg| + |db| in one VABSDIFF4 (the fourth byte of both words is zero).  The second gather goes to an
+// array of at most 512 KB that lives in L1 / L2: measured free next to the table gather (a shared-memory copy of the
+// colours was tried and bought nothing: 107 vs 105 us at 30 000 tiles with one 1024-thread CTA per SM, 93 vs 93 us at 4096).
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 0 ? 1024 : 256)
+__global__ void __launch_bounds__(256)
     match_index16_kernel(const uint8_t *__restrict__ src, const uint16_t *__restrict__ lut16, const uint32_t *__restrict__ colors,
-                         const uint2 *__restrict__ entry, uint32_t slots, uint32_t Q, int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
-    extern __shared__ uint32_t s_col[];
+                         const uint2 *__restrict__ entry, uint32_t Q, int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
     const uint32_t groups = Q >> 2;  // the launcher sends multiples of 4 pixels here and the tail to the wide kernel's scalar path
     const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
     grid_dependency_wait();  // everything below may depend on the previous kernel of the stream (index build, item map readers)
-    if (MODE == 0) {
-        for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) s_col[i] = __ldg(colors + i) & 0xFFFFFFu;
-        __syncthreads();
-    }
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
         const uint32_t q0 = g << 2;
         const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (size_t)g * 3;
@@ -291,10 +285,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 1024 : 256)
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             uint32_t col;
-            if (MODE == 0) {
-                col = s_col[sl[m]];
-                it[m] = sl[m] + 1;
-            } else if (MODE == 1) {
+            if (MODE == 1) {
                 col = __ldg(colors + sl[m]) & 0xFFFFFFu;
                 it[m] = sl[m] + 1;
             } else {
@@ -312,20 +303,9 @@ __global__ void __launch_bounds__(MODE == 0 ? 1024 : 256)
 template <int MODE>
 static int launch_index16(emo_ctx *ctx, const uint8_t *src, uint32_t Q4, int32_t *item, uint32_t *dist) {
     const uint32_t groups = Q4 >> 2;
-    if (MODE == 0) {
-        const size_t smem = (size_t)ctx->lut16_slots * 4;
-        // per device, and a group drives several from one process: set on every launch like the other kernels here
-        EMO_CK(cudaFuncSetAttribute(match_index16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDX16_SMEM_SLOTS * 4)));
-        // one resident CTA per SM when the colours take more than half of the shared memory, two otherwise
-        const uint32_t per_sm = smem > 110 * 1024 ? 1 : 2;
-        const uint32_t blocks = min((groups + 1023) / 1024, (uint32_t)ctx->sm_count * per_sm);
-        EMO_CK(emo_launch_pdl(match_index16_kernel<0>, dim3(blocks), dim3(1024), smem, ctx->stream, src, (const uint16_t *)ctx->lut16,
-                              (const uint32_t *)ctx->cand, (const uint2 *)nullptr, ctx->lut16_slots, Q4, item, dist));
-    } else {
-        const uint32_t blocks = min((groups + 255) / 256, (uint32_t)ctx->sm_count * 8 * 4);
-        EMO_CK(emo_launch_pdl(match_index16_kernel<MODE>, dim3(blocks), dim3(256), 0, ctx->stream, src, (const uint16_t *)ctx->lut16,
-                              (const uint32_t *)ctx->cand, (const uint2 *)ctx->idx_entry, ctx->lut16_slots, Q4, item, dist));
-    }
+    const uint32_t blocks = min((groups + 255) / 256, (uint32_t)ctx->sm_count * 8 * 4);
+    EMO_CK(emo_launch_pdl(match_index16_kernel<MODE>, dim3(blocks), dim3(256), 0, ctx->stream, src, (const uint16_t *)ctx->lut16,
+                          (const uint32_t *)ctx->cand, (const uint2 *)ctx->idx_entry, Q4, item, dist));
     EMO_LAUNCH_CHECK(ctx);
     return EMO_OK;
 }
@@ -348,25 +328,12 @@ static int launch_index32(emo_ctx *ctx, const uint8_t *src, uint32_t Q, int32_t 
 
 int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist) {
     const uint32_t Q = W * H;  // dim == 1: the source is a flat run of Q pixels
-    // which table: EMO_MATCH_INDEX_WIDE / EMO_MATCH_INDEX_COMPACT force one (tuning, tests); otherwise the compact table whenever its second
-    // lookup is free (colours in shared memory and enough pixels per SM to pay for staging them) or the launch is small
-    // enough that a cold 64 MiB table would dominate (a stripe of a multi-GPU run); the 64 MiB table for the rest.
-    const int forced = ctx->match_mode == EMO_MATCH_INDEX_WIDE ? 32 : ctx->match_mode == EMO_MATCH_INDEX_COMPACT ? 16 : 0;
+    // The compact table whenever it exists and the buffers allow word accesses (measured on C4: 97 vs 105 us for 16.7 M pixels,
+    // 20.8 vs 28.1 us for a 2 M-pixel stripe); EMO_MATCH_INDEX_WIDE forces the 64 MiB table (tests, tuning).
     const bool aligned = (uintptr_t)src % 4 == 0 && (uintptr_t)item % 16 == 0 && (uintptr_t)dist % 16 == 0;
-    int mode = -1;  // -1: the 64 MiB table
-    if (ctx->lut16_mode != 0 && aligned && Q >= 4 && forced != 32) {
-        const uint64_t per_sm = (uint64_t)Q / (uint64_t)ctx->sm_count;
-        if (ctx->lut16_mode == 1) {
-            if (ctx->lut16_slots <= IDX16_SMEM_SLOTS && (per_sm >= 2ull * ctx->lut16_slots || (forced == 16 && ctx->lut16_slots > 8192))) mode = 0;
-            else if (forced == 16 || Q <= (6u << 20) || ctx->lut16_slots <= 8192) mode = 1;
-        } else if (forced == 16 || Q <= (6u << 20)) {
-            mode = 2;
-        }
-    }
-    if (mode < 0) return launch_index32(ctx, src, Q, item, dist);
+    if (ctx->lut16_mode == 0 || !aligned || Q < 4 || ctx->match_mode == EMO_MATCH_INDEX_WIDE) return launch_index32(ctx, src, Q, item, dist);
     const uint32_t Q4 = Q & ~3u;
-    int rc = mode == 0 ? launch_index16<0>(ctx, src, Q4, item, dist) : mode == 1 ? launch_index16<1>(ctx, src, Q4, item, dist)
-                                                                               : launch_index16<2>(ctx, src, Q4, item, dist);
+    int rc = ctx->lut16_mode == 1 ? launch_index16<1>(ctx, src, Q4, item, dist) : launch_index16<2>(ctx, src, Q4, item, dist);
     if (rc || Q4 == Q) return rc;
     return launch_index32(ctx, src + (size_t)Q4 * 3, Q - Q4, item + Q4, dist + Q4);  // the last 1..3 pixels
 }

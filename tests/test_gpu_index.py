@@ -106,7 +106,7 @@ def test_index_auto_rule_and_errors(ictx):
     big = rng.integers(0, 256, (2100, 2100, 3), dtype=np.uint8)   # 4.4 M x 2000 >= 2^31: index built, then used
     n0 = ictx.launch_count()
     bi, bd = ictx.match(big)
-    assert ictx.launch_count() - n0 == 5  # seed + 3 sweeps + lookup
+    assert ictx.launch_count() - n0 == 6  # seed + 3 sweeps + compaction to the 32 MiB form + lookup
     n0 = ictx.launch_count()
     i2, d2 = ictx.match(src)              # the index exists now: lookup
     assert ictx.launch_count() - n0 == 1
@@ -303,10 +303,10 @@ def _palette_library(T, P, seed):
 
 
 @pytest.mark.parametrize("T,P,H,W,why", [
-    (300, 0, 96, 128, "slot = tile, colours gathered from global (few pixels per SM)"),
-    (300, 0, 1024, 4096, "slot = tile, colours staged in shared memory"),
-    (40_000, 0, 64, 4096, "slot = tile, 160 KB of colours in shared memory (forced)"),
-    (60_000, 0, 128, 1024, "slot = tile, too many colours for shared memory"),
+    (300, 0, 96, 128, "slot = tile, small launch"),
+    (300, 0, 1024, 4096, "slot = tile, 4 M pixels"),
+    (40_000, 0, 64, 4096, "slot = tile, 160 KB of colours"),
+    (60_000, 0, 128, 1024, "slot = tile, 240 KB of colours"),
     (65_536, 0, 64, 512, "largest library whose tile index fits a slot"),
     (100_000, 40_000, 256, 4096, "more tiles than slots: compacted to the distinct winners"),
     (70_000, 0, 64, 512, "more than 65 536 distinct colours: falls back to the 64 MiB table"),

@@ -22,7 +22,7 @@ ctx.set_match_mode(MODE)
 ctx.build_index(); ctx.sync()
 fused = os.environ.get("FUSED", "0") == "1"   # one emo_mosaic_dev call per step instead of match_dev + compose_dev
 base = None
-for n in (1, 2, 4, 8):
+for n in ([int(x) for x in os.environ['NS'].split(',')] if os.environ.get('NS') else (1, 2, 4, 8)):
     Hs = H // n
     def step(k=None):
         if fused:
