@@ -16,7 +16,7 @@ EXPORTS = [
     "emo_device_info", "emo_launch_count", "emo_timer_start", "emo_timer_stop", "emo_mark", "emo_mark_elapsed", "emo_dev_alloc", "emo_dev_free",
     "emo_host_alloc", "emo_host_free", "emo_copy_h2d", "emo_copy_d2h", "emo_analyse", "emo_analyse_dev",
     "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_library_info", "emo_build_index",
-    "emo_set_match_mode", "emo_match", "emo_topk", "emo_topk_dev",
+    "emo_set_match_mode", "emo_match", "emo_topk", "emo_topk_dev", "emo_no_repeat",
     "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev",
     "emo_resize", "emo_resize_dev", "emo_resize_taps",
     "emo_stripe_bounds", "emo_host_register", "emo_host_unregister",
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
         "emo_match": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
         "emo_topk": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, i32p, u32p]),
         "emo_topk_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, i32p, u32p]),
+        "emo_no_repeat": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, i32p, u32p, C.POINTER(C.c_uint64)]),
         "emo_match_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, i32p, u32p]),
         "emo_compose": (C.c_int, [vp, i32p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_compose_dev": (C.c_int, [vp, i32p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),

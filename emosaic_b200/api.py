@@ -302,6 +302,20 @@ class Context:
         check(self._lib.emo_topk_dev(self._h, C.c_void_p(src_dev), W, H, first, k, C.c_void_p(exclude_dev or 0), C.c_void_p(item_dev),
                                      C.c_void_p(dist_dev)))
 
+    def no_repeat(self, src, page: int = 0):
+        """emo_no_repeat: the assignment of render_nto1_no_repeat (rendering.rs:262-392): (item [bh,bw] with 0 = unplaced,
+        dist [bh,bw], counters dict).  page = candidates per block of the first page (0: automatic)."""
+        src = _u8(src)
+        if src.ndim != 3 or src.shape[2] != 3:
+            raise EmosaicError(EMO_ERR_ARG, f"src must be [H,W,3], got {src.shape}")
+        H, W = src.shape[:2]
+        d = max(self.dim, 1)
+        item = np.zeros((H // d, W // d), np.int32)
+        dist = np.zeros((H // d, W // d), np.uint32)
+        cnt = (C.c_uint64 * 4)()
+        check(self._lib.emo_no_repeat(self._h, _ptr(src), W, H, page, _ptr(item), _ptr(dist), cnt))
+        return item, dist, {"refill_launches": int(cnt[0]), "blocks_refilled": int(cnt[1]), "heap_pops": int(cnt[2]), "placed": int(cnt[3])}
+
     def match_dev(self, src_dev: int, W: int, H: int, item_dev: int, dist_dev: int):
         check(self._lib.emo_match_dev(self._h, C.c_void_p(src_dev), W, H, C.c_void_p(item_dev), C.c_void_p(dist_dev)))
 
@@ -735,15 +749,13 @@ def render_nto1(source_img, tile_set: TileSet, tile_size: int, no_repeat: bool =
     return RenderResult(image, tile_set, item, dist)
 
 
-def render_nto1_no_repeat(source_img, tile_set: TileSet, tile_size: int, ctx: Context | None = None, page: int = 64) -> RenderResult:
+def render_nto1_no_repeat(source_img, tile_set: TileSet, tile_size: int, ctx: Context | None = None, page: int = 0) -> RenderResult:
     """``render_nto1_no_repeat::<N>`` (rendering.rs:262-401): every block gets the nearest tile that no nearer block has
-    taken; a tile is used once, in either orientation.  The ranked candidate lists (the reference's Scoring phase,
-    nearest_n(100000) per block, :307-321) come from the GPU in pages (emo_topk); the greedy merge (:341-392) runs here:
-    blocks ordered by the distance of their best remaining candidate — ties by the reference's block number
-    n = bx * vtiles + by (:300-301), the canonical order of DESIGN.md — a block whose candidate is taken moves on to its
-    next one; a block that runs out of candidates stays black (:347-351).  The image is composed on the GPU."""
-    import heapq
-
+    taken; a tile is used once, in either orientation.  The whole assignment is one library call (emo_no_repeat: ranked
+    candidate lists from the GPU in pages, the greedy merge of rendering.rs:341-392 on the host inside the library, blocks
+    ordered by (distance, reference block number n = bx * vtiles + by), the canonical order of DESIGN.md); a block that runs
+    out of candidates stays black (:347-351).  The image is composed on the GPU.  page = candidates per block of the first
+    page (0: automatic; small values force the refill path)."""
     source_img = _u8(source_img)
     dim = _isqrt_exact(tile_set.N)
     H, W = source_img.shape[:2]
@@ -756,45 +768,8 @@ def render_nto1_no_repeat(source_img, tile_set: TileSet, tile_size: int, ctx: Co
     if bh * bw > 2 * T:  # rendering.rs:292-298
         raise EmosaicError(EMO_ERR_ARG, f"Insufficient tiles for no-repeat mode: need {bh * bw} tiles but only have {2 * T} available")
     ctx = tile_set.build_kiddo(ctx, tile_size)
-    L = T if tile_set.N == 1 else 2 * T          # candidates per list (the N = 1 mirror twins are never reached)
-    k0 = max(1, min(page, 1024))
-    items, dists = ctx.topk(source_img, 0, k0)
-    lists = [(items[q], dists[q]) for q in range(bh * bw)]      # current page of every block
-    ptr = [0] * (bh * bw)                                        # position inside the page
-    retired = np.zeros(T, np.uint8)                              # tiles placed so far (what the reference removes from the tree)
-    heap = [(int(dists[by * bw + bx, 0]), bx * bh + by, by * bw + bx) for by in range(bh) for bx in range(bw)]
-    heapq.heapify(heap)
-    item = np.zeros(bh * bw, np.int32)
-    dist = np.zeros(bh * bw, np.uint32)
-    used = set()
-    while heap:
-        d, n, q = heapq.heappop(heap)
-        its, ds = lists[q]
-        it = int(its[ptr[q]])
-        if abs(it) not in used:
-            used.add(abs(it))
-            retired[abs(it) - 1] = 1
-            item[q], dist[q] = it, d
-            continue
-        ptr[q] += 1
-        if ptr[q] >= len(its):
-            # page used up: the k nearest candidates among the tiles still free — the reference's refill on the pruned
-            # tree (compute_nearest(n, 10), :384-386).  Everything this block skipped so far was taken, so the list of
-            # free candidates continues exactly where the block stands.  (Refilling other half-consumed blocks in the
-            # same launch was tried and is 10x slower: the pages are re-fetched far more often than they run dry.)
-            if len(used) >= T:
-                continue                                         # out of tiles: the block stays black
-            by, bx = divmod(q, bw)
-            blk = np.ascontiguousarray(source_img[by * dim:(by + 1) * dim, bx * dim:(bx + 1) * dim])
-            pi, pd = ctx.topk(blk, 0, max(1, min(2 * len(its), 1024)), exclude=retired)
-            its, ds = pi[0], pd[0]
-            lists[q] = (its, ds)
-            ptr[q] = 0
-        if int(its[ptr[q]]) == 0:
-            continue                                             # end of the list: nothing left for this block
-        heapq.heappush(heap, (int(ds[ptr[q]]), n, q))
-    item = item.reshape(bh, bw)
-    dist = dist.reshape(bh, bw)
+    member = ctx.members[0] if isinstance(ctx, Group) else ctx       # the merge is sequential: one GPU serves the lists
+    item, dist, _ = member.no_repeat(source_img, page)
     placed = item != 0
     image = ctx.compose(np.where(placed, item, 1).astype(np.int32))
     if not placed.all():                                         # RgbImage::new: unplaced blocks stay black

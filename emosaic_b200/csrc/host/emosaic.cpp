@@ -199,62 +199,13 @@ RenderResult render_nto1_no_repeat(Context &ctx, const Image &source, const Tile
         throw Error(EMO_ERR_ARG, "Insufficient tiles for no-repeat mode: need " + std::to_string(Q) + " tiles but only have " +
                                      std::to_string(2 * T) + " available");
     tile_set.build_kiddo(ctx, tile_size);
-    struct List {
-        std::vector<int32_t> item;
-        std::vector<uint32_t> dist;
-    };
-    const uint32_t k0 = std::max<uint32_t>(1, std::min<uint32_t>(page, 1024));
-    std::vector<int32_t> pi(Q * k0);
-    std::vector<uint32_t> pd(Q * k0);
-    check(emo_topk(ctx.handle(), source.data.data(), source.width, source.height, 0, k0, nullptr, pi.data(), pd.data()));
-    std::vector<List> lists(Q);
-    std::vector<size_t> ptr(Q, 0);  // position inside the block's current page
-    using Entry = std::tuple<uint32_t, uint32_t, uint32_t>;  // (distance, n, block)
-    std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry>> heap;
-    for (uint32_t by = 0; by < bh; by++)
-        for (uint32_t bx = 0; bx < bw; bx++) {
-            const size_t q = (size_t)by * bw + bx;
-            lists[q].item.assign(pi.begin() + q * k0, pi.begin() + (q + 1) * k0);
-            lists[q].dist.assign(pd.begin() + q * k0, pd.begin() + (q + 1) * k0);
-            heap.emplace(lists[q].dist[0], bx * bh + by, (uint32_t)q);
-        }
     RenderResult r;
     r.bw = bw;
     r.bh = bh;
     r.item.assign(Q, 0);
     r.dist.assign(Q, 0);
-    std::vector<uint8_t> retired(T, 0);  // tiles placed so far: what the reference removes from the tree (:366-380)
-    size_t n_retired = 0;
-    std::vector<uint8_t> blk((size_t)dim * dim * 3);
-    while (!heap.empty()) {
-        auto [d, n, q] = heap.top();
-        heap.pop();
-        List &l = lists[q];
-        const int32_t it = l.item[ptr[q]];
-        const size_t a = (size_t)(it < 0 ? -it : it) - 1;
-        if (!retired[a]) {
-            retired[a] = 1;
-            n_retired++;
-            r.item[q] = it;
-            r.dist[q] = d;
-            continue;
-        }
-        if (++ptr[q] >= l.item.size()) {
-            // page used up: the k nearest candidates among the tiles still free — the refill on the pruned tree
-            // (compute_nearest(n, 10), :384-386); everything this block skipped so far was taken
-            if (n_retired >= T) continue;  // out of tiles: the block stays black
-            const uint32_t by = q / bw, bx = q % bw;
-            for (uint32_t row = 0; row < dim; row++)
-                std::memcpy(&blk[(size_t)row * dim * 3], source.pixel(bx * dim, by * dim + row), (size_t)dim * 3);
-            const uint32_t k = (uint32_t)std::max<size_t>(1, std::min<size_t>(2 * l.item.size(), 1024));
-            l.item.resize(k);
-            l.dist.resize(k);
-            check(emo_topk(ctx.handle(), blk.data(), dim, dim, 0, k, retired.data(), l.item.data(), l.dist.data()));
-            ptr[q] = 0;
-        }
-        if (l.item[ptr[q]] == 0) continue;  // end of the list: nothing left for this block
-        heap.emplace(l.dist[ptr[q]], n, q);
-    }
+    // scoring (:307-321), ordering (:323-326) and the greedy loop (:341-392) in one library call
+    check(emo_no_repeat(ctx.handle(), source.data.data(), source.width, source.height, page, r.item.data(), r.dist.data(), nullptr));
     std::vector<int32_t> placed(r.item);
     bool holes = false;
     for (auto &v : placed)

@@ -119,8 +119,8 @@ struct RenderResult {
 };
 RenderResult render_nto1(Context &ctx, const Image &source, const TileSet &tile_set, uint32_t tile_size, bool no_repeat = false,
                          std::optional<double> randomize = std::nullopt, double tint_opacity = 0.0);
-// rendering.rs:262-401; `page` = candidates fetched per block and emo_topk call (lists are refilled on demand)
-RenderResult render_nto1_no_repeat(Context &ctx, const Image &source, const TileSet &tile_set, uint32_t tile_size, uint32_t page = 64);
+// rendering.rs:262-401 (emo_no_repeat); `page` = candidates per block of the first page, 0 = automatic (lists are refilled on demand)
+RenderResult render_nto1_no_repeat(Context &ctx, const Image &source, const TileSet &tile_set, uint32_t tile_size, uint32_t page = 0);
 Image render_random(Context &ctx, const Image &source, const TileSet &tile_set, uint32_t tile_size, uint64_t seed);
 uint8_t tint_alpha(double tint_opacity);  // main.rs:449
 

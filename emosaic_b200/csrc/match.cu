@@ -125,8 +125,16 @@ __device__ __forceinline__ uint32_t sad_vec(const uint32_t (&q)[WORDS], const ui
     return d;
 }
 
+// resident CTAs per SM the register budget is planned for
 template <int WORDS, int R, int NT>
-__global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : (WORDS > 4 ? 3 : (R >= 4 ? 4 : 6)))) match_kernel(const MatchParams p) {
+constexpr int match_min_blocks() {
+    return R >= 8 ? (NT >= 256 ? 2 : 4) : (WORDS > 4 ? 3 : (R >= 4 ? (NT <= 64 ? 8 : 4) : 6));
+}
+
+// WIN: candidates between two argmin checks (the stage size must be a multiple); MINB: resident CTAs per SM the registers
+// are capped for (0: match_min_blocks); UNR: unroll factor of the 4-candidate loop
+template <int WORDS, int R, int NT, int WIN = MATCH_WIN, int MINB = 0, int UNR = MATCH_UNROLL>
+__global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS, R, NT>())) match_kernel(const MatchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage_words = p.chunk * WORDS;
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem);
@@ -200,10 +208,10 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : (WORDS > 4 ? 3 : (R >= 
         mbar_wait(&full[s], (n / MATCH_STAGES) & 1);
         const uint32_t *st = ring + (size_t)s * stage_words;
         const uint32_t cand_base = c * p.chunk;
-        for (uint32_t w0 = 0; w0 < p.chunk; w0 += MATCH_WIN) {
+        for (uint32_t w0 = 0; w0 < p.chunk; w0 += WIN) {
             const uint4 *win = reinterpret_cast<const uint4 *>(st + (size_t)w0 * WORDS);
-#pragma unroll(MATCH_UNROLL)
-            for (int j4 = 0; j4 < MATCH_WIN / 4; j4++) {
+#pragma unroll(UNR)
+            for (int j4 = 0; j4 < WIN / 4; j4++) {
                 // 4 candidates = 4*WORDS words = WORDS x LDS.128 (same address in every lane: broadcast)
                 uint32_t cw[4 * WORDS];
 #pragma unroll
@@ -254,9 +262,9 @@ __global__ void __launch_bounds__(NT + 32, (R >= 8 ? 2 : (WORDS > 4 ? 3 : (R >= 
                 ir = idx[rr];
             }
         const uint4 *wc = reinterpret_cast<const uint4 *>(p.cand + (size_t)ir * WORDS);
-        uint32_t found = MATCH_WIN - 1;
+        uint32_t found = WIN - 1;
         constexpr int GB = WORDS <= 2 ? 4 : (WORDS <= 4 ? 2 : 1);  // groups of 4 candidates loaded per batch
-        for (int g0 = MATCH_WIN / 4 - GB; g0 >= 0; g0 -= GB) {
+        for (int g0 = WIN / 4 - GB; g0 >= 0; g0 -= GB) {
             uint4 buf[GB * WORDS];
 #pragma unroll
             for (int i = 0; i < GB * WORDS; i++) buf[i] = __ldg(wc + g0 * WORDS + i);
@@ -310,9 +318,9 @@ __global__ void match_finalize_kernel(const unsigned long long *__restrict__ key
     dist[i] = (uint32_t)(k >> 32);
 }
 
-template <int WORDS, int R, int NT>
+template <int WORDS, int R, int NT, int WIN = MATCH_WIN, int MINB = 0, int UNR = MATCH_UNROLL>
 static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
-    auto kern = match_kernel<WORDS, R, NT>;
+    auto kern = match_kernel<WORDS, R, NT, WIN, MINB, UNR>;
     const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8;
     EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
@@ -326,7 +334,8 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     uint32_t splits = 1;
     if (qtiles < 3 * slots) {
         const uint32_t by_fill = (3 * slots + qtiles - 1) / qtiles;
-        const uint32_t by_len = (p.n_chunks * p.chunk) / 16384u;
+        static const uint32_t min_len = getenv("EMO_MATCH_MINLEN") ? (uint32_t)atoi(getenv("EMO_MATCH_MINLEN")) : 16384u;  // tuning override
+        const uint32_t by_len = (p.n_chunks * p.chunk) / (WORDS == 1 ? 16384u : min_len);
         splits = by_fill < by_len ? by_fill : by_len;
         if (splits < 1) splits = 1;
         if (splits > p.n_chunks) splits = p.n_chunks;
@@ -581,6 +590,27 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
     if (const char *e = getenv("EMO_MATCH_R")) shape = atoi(e);  // tuning override
     if (ctx->words == 1 && shape == 4) return launch_match_t<1, 4, 128>(ctx, p, Q);
     const bool big = shape >= 8;
+    if (ctx->words == 3) {
+        // tuning override: EMO_MATCH_SHAPE3 = R * 1000 + NT
+        static const int shape3 = getenv("EMO_MATCH_SHAPE3") ? atoi(getenv("EMO_MATCH_SHAPE3")) : 0;
+        switch (shape3) {
+            case 2128: return launch_match_t<3, 2, 128>(ctx, p, Q);
+            case 4064: return launch_match_t<3, 4, 64>(ctx, p, Q);
+            case 4128: return launch_match_t<3, 4, 128>(ctx, p, Q);
+            case 8064: return launch_match_t<3, 8, 64>(ctx, p, Q);
+            case 8128: return launch_match_t<3, 8, 128>(ctx, p, Q);
+            case 8256: return launch_match_t<3, 8, 256>(ctx, p, Q);
+            // variants of the <3, 2, 128> shape: window length, register cap, unroll
+            case 1: if (p.chunk % 256 == 0) return launch_match_t<3, 2, 128, 256, 0, 8>(ctx, p, Q); break;
+            case 2: return launch_match_t<3, 2, 128, 128, 0, 4>(ctx, p, Q);
+            case 3: return launch_match_t<3, 2, 128, 128, 0, 16>(ctx, p, Q);
+            case 4: return launch_match_t<3, 2, 128, 128, 7, 8>(ctx, p, Q);
+            case 5: return launch_match_t<3, 2, 128, 128, 5, 8>(ctx, p, Q);
+            case 6: if (p.chunk % 256 == 0) return launch_match_t<3, 2, 128, 256, 7, 8>(ctx, p, Q); break;
+            case 7: if (p.chunk % 256 == 0) return launch_match_t<3, 2, 128, 256, 5, 16>(ctx, p, Q); break;
+            default: break;
+        }
+    }
     switch (ctx->words) {
         case 1: return big ? launch_match_t<1, 8, 256>(ctx, p, Q) : launch_match_t<1, 2, 128>(ctx, p, Q);
         case 3: return big ? launch_match_t<3, 8, 256>(ctx, p, Q) : launch_match_t<3, 2, 128>(ctx, p, Q);

@@ -186,6 +186,21 @@ int emo_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t 
 int emo_topk_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, uint32_t first, uint32_t k,
                  const uint8_t *exclude_dev, int32_t *item_out_dev, uint32_t *dist_out_dev);
 
+/* ---- (3c) no-repeat assignment ---------------------------------------------------------------
+ * Replaces the scoring + greedy loop of render_nto1_no_repeat (src/mosaic/rendering.rs:262-392) in one call: every block
+ * gets the nearest tile that no nearer block has taken; a tile is used once, in either orientation (:357-358).  Blocks are
+ * served in increasing (distance of their best remaining candidate, block number n = bx * vtiles + by) order — the
+ * reference's sorted vector (:323-326, :380-391) with this library's canonical order among equal distances.
+ * The ranked lists come from the GPU (the kernel behind emo_topk): a deep first page for every block, and one batched launch
+ * per refill epoch for the blocks that run dry (filtered by the tiles already placed, like the reference's pruned tree,
+ * :384-386); the sequential merge runs on the host inside this call.
+ * src [H,W,3] host; item / dist [H/dim, W/dim] host; item 0 = the block ran out of candidates and stays black (:347-351).
+ * page: candidates per block of the first page, 0 = as deep as a 512 MB host budget allows (at most 1024).
+ * counters (NULL or [4]): refill launches, blocks refilled, heap pops, tiles placed.
+ * EMO_ERR_ARG when there are more blocks than 2T candidates (:292-298); N = 1, 4, 9, 16 like emo_topk. */
+int emo_no_repeat(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t page, int32_t *item, uint32_t *dist,
+                  uint64_t *counters);
+
 /* ---- (4) compose (+tint) -----------------------------------------------------------------
  * Replaces render() (src/mosaic/rendering.rs:51-101) + TileSet::get_image()
  * (tiles/tileset.rs:146-161) and, when out_channels == 4, the tint block

@@ -153,6 +153,22 @@ def match(colors, src):
     return item, dist
 
 
+def no_repeat_assign(colors, src):
+    """rendering.rs:262-392 up to the placement of tiles (C restatement; oracle_np.no_repeat_assign is the independent numpy
+    one): colors [T,N,3], src [H,W,3] -> (item [bh,bw] int32 with 0 = unplaced, dist [bh,bw] uint32)."""
+    colors, src = _u8(colors), _u8(src)
+    T, N = colors.shape[0], colors.shape[1]
+    dim = int(round(N ** 0.5))
+    H, W = src.shape[:2]
+    if (H // dim) * (W // dim) > 2 * T:
+        raise OracleError(f"Insufficient tiles for no-repeat mode: need {(H // dim) * (W // dim)} tiles but only have {2 * T} available")
+    item = np.zeros((H // dim, W // dim), np.int32)
+    dist = np.zeros((H // dim, W // dim), np.uint32)
+    _chk(lib().orc_no_repeat(_p(colors), C.c_uint32(T), C.c_uint32(N), _p(src), C.c_uint32(W), C.c_uint32(H),
+                             _p(item, i32p), _p(dist, u32p)))
+    return item, dist
+
+
 class KdTree:
     """Bucketed (640) L1 KD-tree over the mirrored candidate set — the reference's algorithm class."""
 

@@ -221,6 +221,95 @@ int orc_match(const uint8_t *colors, uint32_t T, uint32_t N,
     return err;
 }
 
+/* ---- rendering.rs:262-392 render_nto1_no_repeat, up to the placement of tiles -------------------------
+ * Scoring (:307-321): every block's candidates (the whole search set, +idx then -idx per tile) nearest first — here a
+ * stable counting sort by distance, so equal distances stay in insertion rank (canonical; kiddo's nearest_n order among
+ * equal distances is unpinned).  Selection (:323-392): the reference keeps the blocks sorted by the distance of their best
+ * remaining candidate, pops the nearest, places the tile if neither orientation is used (:353-358), else advances the
+ * block and re-inserts it (:380-391).  Equivalent merge with a binary heap on (distance, n), n = bx * vtiles + by the
+ * reference's block number (:300-301, :308-309) — the canonical order among equal distances.  A block whose list is
+ * exhausted stays unplaced: item 0 (:347-351).  Memory: 4 bytes per (block, candidate). */
+typedef struct { uint32_t d, n; } orc_nr_key;
+static inline int nr_less(orc_nr_key a, orc_nr_key b) { return a.d < b.d || (a.d == b.d && a.n < b.n); }
+
+int orc_no_repeat(const uint8_t *colors, uint32_t T, uint32_t N, const uint8_t *src, uint32_t W, uint32_t H,
+                  int32_t *item, uint32_t *dist) {
+    uint32_t dim = isqrt_u32(N), D = 3 * N;
+    if (dim * dim != N || dim == 0 || W % dim || H % dim) return ORC_ERR_ARG;
+    uint32_t L = 2 * T, bw = W / dim, bh = H / dim;
+    uint64_t Q = (uint64_t)bw * bh;
+    if (Q > L) return ORC_ERR_ARG;  /* :292-298 "Insufficient tiles for no-repeat mode" */
+    uint8_t *cand = (uint8_t *)malloc((size_t)L * D + 1);
+    int32_t *items = (int32_t *)malloc((size_t)L * sizeof(int32_t) + 4);
+    orc_build_candidates(colors, T, N, cand, items);
+    uint32_t *order = (uint32_t *)malloc((size_t)Q * L * sizeof(uint32_t));   /* candidate ranks, nearest first */
+    uint32_t maxd = 255 * D;
+    #pragma omp parallel
+    {
+        uint8_t *q = (uint8_t *)malloc(D);
+        uint32_t *dd = (uint32_t *)malloc((size_t)L * sizeof(uint32_t));
+        uint32_t *cnt = (uint32_t *)malloc((size_t)(maxd + 2) * sizeof(uint32_t));
+        #pragma omp for schedule(dynamic, 4)
+        for (int64_t b = 0; b < (int64_t)Q; b++) {
+            uint32_t by = (uint32_t)(b / bw), bx = (uint32_t)(b % bw);
+            orc_get_img_colors(src, W, bx * dim, by * dim, dim, N, q);
+            memset(cnt, 0, (size_t)(maxd + 2) * sizeof(uint32_t));
+            for (uint32_t c = 0; c < L; c++) { dd[c] = l1_u8(cand + (size_t)c * D, q, D); cnt[dd[c] + 1]++; }
+            for (uint32_t v = 0; v <= maxd; v++) cnt[v + 1] += cnt[v];
+            uint32_t *o = order + (size_t)b * L;
+            for (uint32_t c = 0; c < L; c++) o[cnt[dd[c]]++] = c;          /* stable: ranks ascend inside one distance */
+        }
+        free(q); free(dd); free(cnt);
+    }
+    /* selection */
+    orc_nr_key *heap = (orc_nr_key *)malloc((size_t)(Q + 1) * sizeof(orc_nr_key));
+    uint32_t *ptr = (uint32_t *)calloc((size_t)Q + 1, sizeof(uint32_t));
+    uint8_t *used = (uint8_t *)calloc((size_t)T + 1, 1);
+    uint8_t *qv = (uint8_t *)malloc(D);
+    size_t hn = 0;
+    #define NR_DIST(b, c) (orc_get_img_colors(src, W, ((b) % bw) * dim, ((b) / bw) * dim, dim, N, qv), l1_u8(cand + (size_t)(c) * D, qv, D))
+    for (uint64_t b = 0; b < Q; b++) {
+        item[b] = 0; dist[b] = 0;
+        uint32_t by = (uint32_t)(b / bw), bx = (uint32_t)(b % bw);
+        orc_nr_key k = { NR_DIST(b, order[(size_t)b * L]), bx * bh + by };
+        size_t i = hn++;                                                   /* sift up */
+        while (i > 0 && nr_less(k, heap[(i - 1) / 2])) { heap[i] = heap[(i - 1) / 2]; i = (i - 1) / 2; }
+        heap[i] = k;
+    }
+    while (hn > 0) {
+        orc_nr_key top = heap[0];
+        orc_nr_key last = heap[--hn];                                      /* pop: sift the last element down from the root */
+        size_t i = 0;
+        for (;;) {
+            size_t l = 2 * i + 1, r = l + 1, m = i;
+            orc_nr_key best = last;
+            if (l < hn && nr_less(heap[l], best)) { best = heap[l]; m = l; }
+            if (r < hn && nr_less(heap[r], best)) { best = heap[r]; m = r; }
+            if (m == i) break;
+            heap[i] = heap[m]; i = m;
+        }
+        if (hn > 0) heap[i] = last;
+        uint32_t bx = top.n / bh, by = top.n % bh;
+        uint64_t b = (uint64_t)by * bw + bx;
+        uint32_t c = order[(size_t)b * L + ptr[b]];
+        uint32_t t = c >> 1;
+        if (!used[t]) {
+            used[t] = 1;                                                   /* both orientations retire (:357-358) */
+            item[b] = items[c];
+            dist[b] = top.d;
+            continue;
+        }
+        if (++ptr[b] >= L) continue;                                       /* out of candidates: stays black */
+        orc_nr_key k = { NR_DIST(b, order[(size_t)b * L + ptr[b]]), top.n };
+        i = hn++;
+        while (i > 0 && nr_less(k, heap[(i - 1) / 2])) { heap[i] = heap[(i - 1) / 2]; i = (i - 1) / 2; }
+        heap[i] = k;
+    }
+    #undef NR_DIST
+    free(qv); free(used); free(ptr); free(heap); free(order); free(cand); free(items);
+    return ORC_OK;
+}
+
 /* ---- bucketed KD-tree, L1, leaf capacity 640 ---------------------------- */
 /* The reference's algorithm class (kiddo KdTree<_, i16, 3N, 640, u16> + nearest_one),
  * restated with the canonical tie-break so its answers equal orc_match exactly:

@@ -141,6 +141,45 @@ def test_render_no_repeat_contention(ctx):
     assert (res.image == oracle.render(tiles, ri)).all()
 
 
+@pytest.mark.parametrize("N,T,bh,bw,page", [(4, 5000, 60, 60, 0), (4, 5000, 60, 60, 8), (1, 3000, 50, 60, 0), (1, 3000, 50, 60, 2),
+                                            (9, 2000, 30, 40, 16)])
+def test_no_repeat_assignment_large(ctx, N, T, bh, bw, page):
+    """emo_no_repeat against the C oracle at sizes where pages run dry in bulk (batched refills) and with the automatic deep
+    first page; the refill path must have been exercised when the page is small."""
+    dim = int(N ** 0.5)
+    rng = np.random.default_rng(N + T)
+    colors = rng.integers(0, 256, (T, N, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (bh * dim, bw * dim, 3), dtype=np.uint8)
+    ctx.set_library(colors)
+    item, dist, cnt = ctx.no_repeat(src, page)
+    ri, rd = oracle.no_repeat_assign(colors, src)
+    assert (item == ri).all() and (dist == rd).all()
+    assert cnt["placed"] == (ri != 0).sum()
+    if page and page <= 8:
+        assert cnt["refill_launches"] > 0 and cnt["blocks_refilled"] >= cnt["refill_launches"]
+
+
+def test_no_repeat_120x120_blocks_from_20k_tiles(ctx):
+    """The size DESIGN.md quotes (a 120 x 120-block render from 20 000 tiles, 4to1): parity with the C oracle, every tile at most
+    once, and the whole assignment (lists + merge) well under a second (it took 5 s while the merge lived in Python)."""
+    import time
+    rng = np.random.default_rng(120)
+    T = 20_000
+    colors = rng.integers(0, 256, (T, 4, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (240, 240, 3), dtype=np.uint8)
+    ctx.set_library(colors)
+    ctx.no_repeat(src[:8, :8])                                # warm-up (buffers)
+    t0 = time.perf_counter()
+    item, dist, cnt = ctx.no_repeat(src)
+    dt = time.perf_counter() - t0
+    print(f"no_repeat 120x120 blocks / 20k tiles: {dt * 1e3:.1f} ms, {cnt}")
+    assert dt < 1.0, f"{dt:.2f} s"
+    used = np.abs(item[item != 0])
+    assert used.size == 14400 and len(set(used.tolist())) == used.size
+    ri, rd = oracle.no_repeat_assign(colors, src)             # 2.3 GB of candidate order on the host
+    assert (item == ri).all() and (dist == rd).all()
+
+
 @pytest.mark.parametrize("N", [1, 4, 9])
 def test_universe_no_repeat_gpu(ctx, N):
     """mod.rs:118-145 through the CUDA path."""

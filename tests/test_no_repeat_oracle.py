@@ -81,3 +81,20 @@ def test_properties_and_errors():
     assert (item == 0).sum() == 10 and len(set(np.abs(item[item != 0]).tolist())) == 15
     with pytest.raises(AssertionError, match="Insufficient tiles for no-repeat mode: need 25 tiles but only have 24"):
         onp.no_repeat_assign(colors[:12], src)
+
+
+@pytest.mark.parametrize("N,T,bh,bw,quant", [(1, 400, 12, 15, 1), (4, 150, 8, 9, 1), (9, 60, 4, 5, 1), (4, 90, 9, 10, 64), (1, 30, 6, 10, 1),
+                                             (4, 40, 8, 10, 32), (16, 25, 3, 4, 1), (1, 2000, 40, 45, 8)])
+def test_c_oracle_equals_numpy_oracle(N, T, bh, bw, quant):
+    """The C restatement (oracle.no_repeat_assign: counting-sorted lists + heap merge, sized for 120 x 120 blocks) and the
+    independent numpy one agree, including quantised colours (competing equal distances) and libraries too small to fill the
+    image (T < blocks <= 2T: the rest stays unplaced)."""
+    dim = int(N ** 0.5)
+    rng = np.random.default_rng(N * 100 + T)
+    colors = (rng.integers(0, 256, (T, N, 3)) // quant * quant).astype(np.uint8)
+    src = (rng.integers(0, 256, (bh * dim, bw * dim, 3)) // quant * quant).astype(np.uint8)
+    ci, cd = oracle.no_repeat_assign(colors, src)
+    ni, nd = onp.no_repeat_assign(colors, src)
+    assert (ci == ni).all() and (cd == nd).all()
+    with pytest.raises(AssertionError, match="Insufficient tiles"):
+        oracle.no_repeat_assign(colors[:1], src)
