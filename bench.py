@@ -277,19 +277,21 @@ def run_ours(args):
     index_build_ms = float(np.median(idx_ms))
 
     def step(k=None, base=0):
-        """match + compose of the stripe; k = slot of the CUDA-event marks around the two launches (None: no marks)."""
-        if k is not None:
-            ctx.mark(base + 3 * k)
+        """match + compose of the stripe.  k = None: one emo_mosaic_dev call (the two launches back to back).  k = slot of the
+        CUDA-event marks around the two launches: emo_match_dev, mark, emo_compose_dev — the per-kernel durations of the roofline."""
+        if k is None:
+            ctx.mosaic_dev(src_ptr, W, Hs, 3, 0, item_d.data_ptr(), dist_d.data_ptr(), out_d.data_ptr())
+            return
+        ctx.mark(base + 3 * k)
         ctx.match_dev(src_ptr, W, Hs, item_d.data_ptr(), dist_d.data_ptr())
-        if k is not None:
-            ctx.mark(base + 3 * k + 1)
+        ctx.mark(base + 3 * k + 1)
         ctx.compose_dev(item_d.data_ptr(), 0, W, Hs, 3, 0, out_d.data_ptr())
-        if k is not None:
-            ctx.mark(base + 3 * k + 2)
+        ctx.mark(base + 3 * k + 2)
 
-    # Per-kernel CUDA events inside the timed region: every step at N = 1 (the roofline line).  An event record between
-    # two kernels costs ~3 us of stream time, which is 8 % of a 90 us step at N = 8, so multi-GPU runs mark two steps only.
-    marked = list(range(args.steps)) if world == 1 else sorted({0, args.steps - 1})
+    # Per-kernel CUDA events inside the timed region on two of the timed steps, at every N.  An event record between two
+    # kernels serialises them (no programmatic overlap) and costs about 6 us of stream time per record: 12 us per step, 2 % of
+    # the 0.6 ms step at N = 1 and 15 % of the 80 us step at N = 8 (tools/bench_stripes.py with and without marks).
+    marked = sorted({0, args.steps - 1})
 
     for _ in range(args.warmup):
         step()
@@ -359,19 +361,35 @@ def run_ours(args):
     if not args.no_extras:
         from tools import probe
         stripe_out = Hs * ts * W * ts * 3
+        reps = 3
+        # every rank starts its timed copies at the same wall-clock instant (the ranks share the box's clock): allocation and
+        # the warm-up pass of 8 x 400 MB of pinned memory take different times per process
         barrier()
-        _, per = probe.host_copy([local_rank], stripe_out, 64 << 20, "d2h", 3)
-        barrier()
-        t_all = max_over_ranks(stripe_out * 3 / (per[0] * 1e9))            # slowest rank's time for its 3 passes
+        t_all, lead = None, 4.0
+        for attempt in range(2):
+            box = [time.time_ns() + int(lead * 1e9) if rank == 0 else None]
+            if world > 1:
+                dist.broadcast_object_list(box, src=0)
+            ok = 1.0
+            try:
+                _, per = probe.host_copy([local_rank], stripe_out, 64 << 20, "d2h", reps, start_unix_ns=box[0])
+                mine = stripe_out * reps / (per[0] * 1e9)
+            except RuntimeError:
+                ok, mine = 0.0, 0.0
+            barrier()
+            if -max_over_ranks(-ok) == 1.0:          # min over ranks: everyone started on time
+                t_all = max_over_ranks(mine)           # slowest rank's time for its passes
+                break
+            lead *= 3
         solo = None
         if rank == 0:
-            _, per0 = probe.host_copy([local_rank], stripe_out, 64 << 20, "d2h", 3)
+            _, per0 = probe.host_copy([local_rank], stripe_out, 64 << 20, "d2h", reps)
             solo = per0[0]
         barrier()
-        host = {"d2h_all_ranks_gbs": H * ts * W * ts * 3 * 3 / t_all / 1e9, "d2h_one_rank_alone_gbs": solo,
+        host = {"d2h_all_ranks_gbs": (H * ts * W * ts * 3 * reps / t_all / 1e9) if t_all else None, "d2h_one_rank_alone_gbs": solo,
                 "bytes_per_rank": stripe_out, "piece": 64 << 20,
-                "note": "pinned cudaHostAlloc buffers, every rank copying its stripe-sized buffer device->host at once "
-                        "(tools/probe/hostcopy.cu); aggregate = whole-image bytes / slowest rank's time"}
+                "note": "pinned cudaHostAlloc buffers, every rank copying a buffer of its stripe's size device->host, all ranks starting "
+                        "at the same wall-clock instant (tools/probe/hostcopy.cu); aggregate = whole-image bytes / slowest rank's time"}
 
     # ---- context for the strong-scaling number: the same step with a whole 4096 x 4096 source per rank (weak scaling) ----
     weak = None
@@ -495,7 +513,7 @@ def run_ours(args):
                "d2h_gbs": d2h_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9}
         if host is not None:
             e2e["host_d2h_ceiling_gbs"] = host["d2h_all_ranks_gbs"]
-            e2e["frac_of_host_ceiling"] = e2e["d2h_gbs"] / host["d2h_all_ranks_gbs"]
+            e2e["frac_of_host_ceiling"] = e2e["d2h_gbs"] / host["d2h_all_ranks_gbs"] if host["d2h_all_ranks_gbs"] else None
             e2e["host_ceiling"] = host
         line = {
             "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -576,27 +594,28 @@ def c2_record(ctx, emo, torch, dev, world, rank, args, max_over_ranks, barrier, 
     def step(k=None):
         if rows == 0:
             return
-        if k is not None:
-            ctx.mark(base + 3 * k)
+        if k is None:
+            ctx.mosaic_dev(src_d.data_ptr(), S2, rows * dim, 3, 0, item_d.data_ptr(), dist_d.data_ptr(), out_d.data_ptr())
+            return
+        ctx.mark(base + 3 * k)
         ctx.match_dev(src_d.data_ptr(), S2, rows * dim, item_d.data_ptr(), dist_d.data_ptr())
-        if k is not None:
-            ctx.mark(base + 3 * k + 1)
+        ctx.mark(base + 3 * k + 1)
         ctx.compose_dev(item_d.data_ptr(), 0, S2, rows * dim, 3, 0, out_d.data_ptr())
-        if k is not None:
-            ctx.mark(base + 3 * k + 2)
+        ctx.mark(base + 3 * k + 2)
 
+    marked = sorted({0, args.steps - 1})      # per-kernel events on two of the timed steps, like the headline
     for _ in range(max(args.warmup, 3)):
         step()
     ctx.sync()
     barrier()
     ctx.timer_start()
     for k in range(args.steps):
-        step(k)
+        step(k if k in marked else None)
     ms = ctx.timer_stop()
     barrier()
     ms = max_over_ranks(ms)
-    m_ms = float(np.mean([ctx.mark_elapsed(base + 3 * k, base + 3 * k + 1) for k in range(args.steps)])) if rows else 0.0
-    c_ms = float(np.mean([ctx.mark_elapsed(base + 3 * k + 1, base + 3 * k + 2) for k in range(args.steps)])) if rows else 0.0
+    m_ms = float(np.mean([ctx.mark_elapsed(base + 3 * k, base + 3 * k + 1) for k in marked])) if rows else 0.0
+    c_ms = float(np.mean([ctx.mark_elapsed(base + 3 * k + 1, base + 3 * k + 2) for k in marked])) if rows else 0.0
     m_ms_max, c_ms_max = max_over_ranks(m_ms), max_over_ranks(c_ms)
     # e2e: host stripe in, host stripe out
     e2e_steps = 3

@@ -1,5 +1,6 @@
 // ctx.cu — context management and the host-pointer halves of the C ABI (include/emosaic_cuda.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"

@@ -21,6 +21,8 @@ def load():
         lib.emo_probe_host_copy.restype = C.c_int
         lib.emo_probe_host_copy.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.emo_probe_host_copy_at.restype = C.c_int
+        lib.emo_probe_host_copy_at.argtypes = lib.emo_probe_host_copy.argtypes + [C.c_int64]
         _lib = lib
     return _lib
 
@@ -34,13 +36,18 @@ def probe_int_pipe(device: int, which: int) -> float:
     return float(v.value)
 
 
-def host_copy(devices, nbytes: int, chunk: int = 64 << 20, direction: str = "d2h", reps: int = 3):
-    """(aggregate GB/s, [per-device GB/s]) of pinned-memory copies with every listed device copying at the same time."""
+def host_copy(devices, nbytes: int, chunk: int = 64 << 20, direction: str = "d2h", reps: int = 3, start_unix_ns: int = 0):
+    """(aggregate GB/s, [per-device GB/s]) of pinned-memory copies with every listed device copying at the same time.
+    start_unix_ns: wall-clock instant at which the timed copies start (several processes on one box: every rank passes the
+    same instant); raises if the set-up finished after it."""
     devices = list(devices)
     arr = (C.c_int * len(devices))(*devices)
     agg = C.c_double()
     per = (C.c_double * len(devices))()
-    rc = load().emo_probe_host_copy(arr, len(devices), nbytes, chunk, 0 if direction == "d2h" else 1, reps, C.byref(agg), per)
-    if rc:
+    rc = load().emo_probe_host_copy_at(arr, len(devices), nbytes, chunk, 0 if direction == "d2h" else 1, reps, C.byref(agg), per,
+                                       int(start_unix_ns))
+    if rc < 0:
         raise RuntimeError(f"emo_probe_host_copy: cudaError {-rc}")
+    if rc == 1:
+        raise RuntimeError("emo_probe_host_copy: set-up finished after the common start instant")
     return float(agg.value), [float(x) for x in per]

@@ -9,6 +9,9 @@
 //   per piece, like emo_mosaic's drain.  dir 0 = device -> host, 1 = host -> device.  All workers start together;
 //   aggregate = n * bytes * reps / (wall time from the common start to the last worker's finish); per-device figures are
 //   CUDA-event times of each worker's own copies.  Returns 0 or a negative cudaError.
+//   emo_probe_host_copy_at(..., start_unix_ns): the same, but the timed copies start at that wall-clock instant
+//   (CLOCK_REALTIME), so that several PROCESSES on one box (one rank per GPU) copy at the same time; returns 1 when the
+//   set-up (allocation, warm-up pass) finished after the instant — the figure would not be a concurrent one.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -18,8 +21,15 @@
 #include <thread>
 #include <vector>
 
-extern "C" int emo_probe_host_copy(const int *devices, int n, size_t bytes, size_t chunk, int dir, int reps, double *aggregate_gbs,
-                                   double *per_device_gbs) {
+#include <time.h>
+static int64_t unix_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    return (int64_t)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+
+extern "C" int emo_probe_host_copy_at(const int *devices, int n, size_t bytes, size_t chunk, int dir, int reps, double *aggregate_gbs,
+                                      double *per_device_gbs, int64_t start_unix_ns) {
     if (n < 1 || n > 64 || bytes == 0 || reps < 1) return -(int)cudaErrorInvalidValue;
     if (chunk == 0 || chunk > bytes) chunk = bytes;
     std::vector<int> rc(n, 0);
@@ -72,6 +82,12 @@ extern "C" int emo_probe_host_copy(const int *devices, int n, size_t bytes, size
     std::vector<std::thread> th;
     for (int i = 0; i < n; i++) th.emplace_back(work, i);
     while (ready.load() < n) std::this_thread::yield();
+    bool late = false;
+    if (start_unix_ns) {
+        late = unix_ns() > start_unix_ns;
+        while (unix_ns() < start_unix_ns) {
+        }
+    }
     const auto t0 = std::chrono::steady_clock::now();
     go.store(1);
     for (auto &t : th) t.join();
@@ -84,5 +100,10 @@ extern "C" int emo_probe_host_copy(const int *devices, int n, size_t bytes, size
         if (per_device_gbs) per_device_gbs[i] = (double)bytes * reps / (ms[i] * 1e-3) / 1e9;
     }
     if (aggregate_gbs) *aggregate_gbs = (double)n * bytes * reps / wall / 1e9;
-    return 0;
+    return late ? 1 : 0;
+}
+
+extern "C" int emo_probe_host_copy(const int *devices, int n, size_t bytes, size_t chunk, int dir, int reps, double *aggregate_gbs,
+                                   double *per_device_gbs) {
+    return emo_probe_host_copy_at(devices, n, bytes, chunk, dir, reps, aggregate_gbs, per_device_gbs, 0);
 }
