@@ -348,6 +348,20 @@ class Context:
         check(self._lib.emo_compose_dev(self._h, C.c_void_p(item_dev), C.c_void_p(src_dev or 0), W, H, out_channels,
                                         tint_alpha, C.c_void_p(out_dev)))
 
+    def stats(self, item, dist, want_usage: bool = True):
+        """emo_stats: the reductions of RenderStats (stats.rs:87-139, :169-175) over a render's maps, on the GPU:
+        {"placed", "total_distance", "max_distance"} and usage [T] (blocks per tile, either orientation)."""
+        item = np.ascontiguousarray(item, dtype=np.int32)
+        dist = np.ascontiguousarray(dist, dtype=np.uint32)
+        sums = np.zeros(3, np.uint64)
+        usage = np.zeros(self.T, np.uint32) if want_usage else None
+        check(self._lib.emo_stats(self._h, _ptr(item), _ptr(dist), item.size, self.T, _ptr(sums), _ptr(usage)))
+        return {"placed": int(sums[0]), "total_distance": int(sums[1]), "max_distance": int(sums[2])}, usage
+
+    def stats_dev(self, item_dev: int, dist_dev: int, Q: int, sums_dev: int, usage_dev: int = 0):
+        check(self._lib.emo_stats_dev(self._h, C.c_void_p(item_dev), C.c_void_p(dist_dev), Q, self.T, C.c_void_p(sums_dev),
+                                      C.c_void_p(usage_dev or 0)))
+
     def mosaic_dev(self, src_dev: int, W: int, H: int, out_channels: int, tint_alpha: int, item_dev: int, dist_dev: int, out_dev: int):
         check(self._lib.emo_mosaic_dev(self._h, C.c_void_p(src_dev), W, H, out_channels, tint_alpha, C.c_void_p(item_dev),
                                        C.c_void_p(dist_dev), C.c_void_p(out_dev)))
@@ -475,6 +489,9 @@ class Group:
 
     def topk(self, *a, **k):
         return self.members[0].topk(*a, **k)
+
+    def stats(self, *a, **k):
+        return self.members[0].stats(*a, **k)
 
 
 def host_register(arr: np.ndarray):

@@ -229,7 +229,7 @@ def main(argv=None) -> int:
             ctx.set_library(colors, px)
             out, item, dist = ctx.mosaic(img, 3, 0)
         placed = item != 0  # the reference records statistics for placed tiles only (rendering.rs:362-365)
-        stats.summarise(item[placed], dist[placed], paths)
+        stats.summarise(item, dist, paths, ctx=ctx)   # counts and sums on the GPU (emo_stats), item 0 = unplaced: no entry
         src_for_tint = original  # main.rs:447-466 overlays the image as opened, not the copy resized for matching
 
     if args.tint_opacity > 0.0:  # main.rs:447-478: RGBA PNG, early return (no stats image)

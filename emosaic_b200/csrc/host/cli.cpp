@@ -161,7 +161,7 @@ int main(int argc, char **argv) {
             write_png(output, rgba);
             return 0;
         }
-        summarise(r, ts);
+        summarise(r, ts, true, &ctx);
         write_png(output, r.image);
         const size_t dot = output.find_last_of('.');
         // the no-repeat renderer keys its statistics by output coordinates (rendering.rs:352-365): one pixel per block

@@ -421,7 +421,7 @@ TileSet deserialize_tile_set(const std::vector<uint8_t> &b, uint32_t N, const st
 }
 
 // ---- stats.rs ---------------------------------------------------------------------------------------
-StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print) {
+StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print, Context *ctx) {
     StatsSummary s;
     // rendering.rs:352-365 records placed tiles only: a no-repeat block that ran out of tiles (item 0) has no entry
     std::vector<size_t> placed;
@@ -434,9 +434,19 @@ StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print) {
     }
     std::map<uint32_t, uint32_t> usage;
     uint64_t sum = 0;
-    for (size_t i : placed) {
-        usage[(uint32_t)std::abs(r.item[i])]++;
-        sum += r.dist[i];
+    if (ctx) {  // one pass over the maps on the GPU (stats.cu)
+        uint64_t sums[3] = {0, 0, 0};
+        std::vector<uint32_t> u(ts.len(), 0);
+        check(emo_stats(ctx->handle(), r.item.data(), r.dist.data(), r.item.size(), (uint32_t)ts.len(), sums, u.data()));
+        for (size_t t = 0; t < u.size(); t++)
+            if (u[t]) usage[(uint32_t)t + 1] = u[t];
+        sum = sums[1];
+        s.total = (size_t)sums[0];
+    } else {
+        for (size_t i : placed) {
+            usage[(uint32_t)std::abs(r.item[i])]++;
+            sum += r.dist[i];
+        }
     }
     s.unique = usage.size();
     s.average_distance = (double)sum / (double)s.total;

@@ -149,7 +149,8 @@ struct StatsSummary {
     double average_distance = 0;
     std::vector<std::pair<std::string, uint32_t>> top, worst;
 };
-StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print = true);
+// ctx: reduce the counts and sums on the GPU (emo_stats) instead of on the host; the two top-10 lists are host work either way
+StatsSummary summarise(const RenderResult &r, const TileSet &ts, bool print = true, Context *ctx = nullptr);
 Image render_stats(const RenderResult &r, uint32_t dim, uint32_t tile_size);
 
 // ---- minimal image I/O for the CLI (PPM P6 and non-interlaced 8-bit PNG over zlib) ---------------------

@@ -315,6 +315,12 @@ int main(int argc, char **argv) {
         int placed = 0;
         for (int32_t it : r.item) placed += it != 0;
         CHECK(placed == 3 && r.item[0] == 1 && r.dist[0] == 0);
+        // the summary with its sums reduced on the GPU (emo_stats) equals the host-only one; unplaced blocks have no entry
+        TileSet named(1);
+        for (const char *p : {"a", "b", "c"}) named.push_tile(p, {0, 0, 0});
+        const StatsSummary host = summarise(r, named, false), dev = summarise(r, named, false, &ctx);
+        CHECK(dev.total == 3 && dev.total == host.total && dev.unique == host.unique && dev.average_distance == host.average_distance);
+        CHECK(dev.top == host.top && dev.worst == host.worst);
     });
     // main.rs:603-615 exits become errors
     run("test_dimension_rules", [&] {

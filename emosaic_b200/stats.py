@@ -64,19 +64,30 @@ class RenderStats:
         return img
 
 
-def summarise(item: np.ndarray, dist: np.ndarray, paths: Optional[Sequence[str]] = None, file=sys.stderr) -> dict:
-    """stats.rs:87-139: totals, unique images, average distance, top-10 usage, worst-10 matches."""
-    if item.size == 0:
+def summarise(item: np.ndarray, dist: np.ndarray, paths: Optional[Sequence[str]] = None, file=sys.stderr, ctx=None) -> dict:
+    """stats.rs:87-139: totals, unique images, average distance, top-10 usage, worst-10 matches.  With `ctx` (a Context whose
+    library is the one the maps refer to) the counts and sums are reduced on the GPU (emo_stats); the two ordered top-10
+    lists are host work either way.  item 0 (an unplaced no-repeat block) has no entry."""
+    item = np.asarray(item)
+    keep = item.reshape(-1) != 0
+    if not keep.any():
         print("No tiles recorded in statistics", file=file)
         return {}
-    ids = np.abs(item).reshape(-1)
-    d = dist.reshape(-1).astype(np.uint64)
-    uniq, counts = np.unique(ids, return_counts=True)
+    ids = np.abs(item.reshape(-1)[keep])
+    d = np.asarray(dist).reshape(-1)[keep].astype(np.uint64)
+    if ctx is not None:
+        sums, usage = ctx.stats(item, dist)
+        uniq = np.nonzero(usage)[0] + 1
+        counts = usage[uniq - 1].astype(np.int64)
+        total, dsum = sums["placed"], sums["total_distance"]
+    else:
+        uniq, counts = np.unique(ids, return_counts=True)
+        total, dsum = int(ids.size), int(d.sum())
     order = np.lexsort((uniq, -counts))[:10]
     worst = np.argsort(-d.astype(np.int64), kind="stable")[:10]
     name = (lambda i: paths[i - 1]) if paths is not None else (lambda i: f"tile #{i}")
     out = {
-        "total": int(ids.size), "unique": int(uniq.size), "average_distance": float(d.sum()) / ids.size,
+        "total": int(total), "unique": int(uniq.size), "average_distance": float(dsum) / total,
         "top": [(name(int(uniq[i])), int(counts[i])) for i in order],
         "worst": [(name(int(ids[i])), int(d[i])) for i in worst],
     }

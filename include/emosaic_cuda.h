@@ -224,6 +224,18 @@ int emo_compose_overlay(emo_ctx *ctx, const int32_t *item, uint32_t W, uint32_t 
 int emo_compose_overlay_dev(emo_ctx *ctx, const int32_t *item_dev, uint32_t W, uint32_t H, const uint8_t *overlay_dev,
                             uint32_t ow, uint32_t oh, uint8_t tint_alpha, uint8_t *out_dev);
 
+/* ---- (5) render statistics from the maps ----------------------------------------------------------
+ * Replaces the accumulation of RenderStats — one push_tile per block under a Mutex (src/mosaic/rendering.rs:211-214,
+ * stats.rs:56-64) — and the reductions summarise() / render() make over it (stats.rs:87-139, :169-175), as one pass over the
+ * item / dist maps a match produced: sums[0] = blocks that carry a tile (item != 0), sums[1] = the sum of their distances,
+ * sums[2] = their largest distance; usage[t] (NULL or [T]) = how many blocks placed tile t + 1, in either orientation.
+ * The two ordered lists of the summary (ten most used, ten worst) are left to the host layers.
+ * emo_stats_dev: device pointers (e.g. the maps emo_match_dev / emo_mosaic_dev just wrote), asynchronous; sums_dev is
+ * three 8-byte aligned uint64.  emo_stats: host pointers, synchronous.  EMO_ERR_ARG for an id beyond T. */
+int emo_stats_dev(emo_ctx *ctx, const int32_t *item_dev, const uint32_t *dist_dev, uint64_t Q, uint32_t T, uint64_t *sums_dev,
+                  uint32_t *usage_dev);
+int emo_stats(emo_ctx *ctx, const int32_t *item, const uint32_t *dist, uint64_t Q, uint32_t T, uint64_t sums[3], uint32_t *usage);
+
 /* ---- whole path ------------------------------------------------------------------------------
  * render_nto1 (+ tint) in one call (rendering.rs:124-239 + main.rs:447-478).
  * emo_mosaic: host buffers; H2D(src) -> match -> compose -> D2H(out) with the copies pipelined

@@ -564,3 +564,31 @@ def test_tint_overlay_of_another_size(ctx, A):
         got = ctx.compose_overlay(item, overlay, A)
         want = oracle.tint(oracle.render(tiles, item), overlay, A)
         assert (got == want).all(), (N, ts, bh, bw, oh, ow)
+
+
+def test_stats_reduction_on_the_gpu(ctx):
+    """emo_stats (the reductions of RenderStats, stats.rs:87-139 / :169-175) against numpy on maps with mirrored ids and unplaced
+    blocks; the summary built from it equals the host-only one; an id beyond the library is rejected."""
+    import io
+    from emosaic_b200 import stats
+    rng = np.random.default_rng(8)
+    T = 777
+    ctx.set_library(rng.integers(0, 256, (T, 4, 3), dtype=np.uint8))
+    item = (rng.integers(1, T + 1, (300, 411)) * rng.choice([-1, 1], (300, 411))).astype(np.int32)
+    item[rng.random(item.shape) < 0.1] = 0
+    item[:, :7] = 5                                   # a heavily used tile
+    dist = rng.integers(0, 3060, item.shape).astype(np.uint32)
+    sums, usage = ctx.stats(item, dist)
+    placed = item != 0
+    assert sums == {"placed": int(placed.sum()), "total_distance": int(dist[placed].astype(np.uint64).sum()),
+                    "max_distance": int(dist[placed].max())}
+    want = np.bincount(np.abs(item[placed]) - 1, minlength=T)
+    assert (usage == want).all()
+    a = stats.summarise(item, dist, None, file=io.StringIO(), ctx=ctx)
+    b = stats.summarise(item, dist, None, file=io.StringIO())
+    assert a == b
+    empty = np.zeros((3, 3), np.int32)
+    assert ctx.stats(empty, empty.astype(np.uint32))[0] == {"placed": 0, "total_distance": 0, "max_distance": 0}
+    bad = item.copy(); bad[0, 0] = T + 1
+    with pytest.raises(emo.EmosaicError):
+        ctx.stats(bad, dist)
