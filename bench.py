@@ -475,15 +475,17 @@ def run_ours(args):
             # index build (the GPU stand-in for that tree) in every step
             "value_per_render": Q_total / ((step_ms + index_build_ms) * 1e-3),
             "composed_output_gbs": (H * ts * W * ts * 3) / (comp_ms_max * 1e-3) / 1e9,
-            "roofline_match_index": {"kernel": "match_index_kernel", "bound": "hbm", "achieved": look_bytes / (match_ms * 1e-3) / 1e9,
+            "roofline_match_index": {"kernel": "match_index16_kernel<2>", "bound": "hbm", "achieved": look_bytes / (match_ms * 1e-3) / 1e9,
                                      "peak": hbm_peak, "unit": "GB/s", "frac": look_bytes / (match_ms * 1e-3) / 1e9 / hbm_peak,
-                                     "traffic": measured_traffic("match_index_kernel", world), "ms_per_launch": match_ms,
-                                     "note": "algorithmic bytes = 11 B per block (3 B of source in, 8 B of item + dist out)"},
+                                     "traffic": measured_traffic("match_index16_kernel", world), "ms_per_launch": match_ms,
+                                     "note": "algorithmic bytes = 11 B per block (3 B of source in, 8 B of item + dist out); the 32 MiB "
+                                             "compact table is gathered from L2; the duration is of an event-bracketed launch (two of "
+                                             "the timed steps), which includes ~5 us of launch latency"},
             "match_scan": {
                 "kernel": "match_kernel<1,8,256>", "bound": "int32-pipe (VABSDIFF4)", "ms_per_launch": scan_ms_max, "steps": scan_steps,
                 "matched_px_per_s": Q_total / ((scan_ms_max + comp_ms_max) * 1e-3),
                 "achieved": pairs_per_s / 1e12, "peak": sad / 1e12, "unit": "T pairs/s", "frac": pairs_per_s / sad,
-                "traffic": measured_traffic("match_kernel", world),
+                "traffic": measured_traffic("match_kernel_c4", world),
                 "note": "the same step with EMO_MATCH_SCAN (the north star's brute-force kernel): achieved = (query, candidate) "
                         "pairs per second of the scan launch; peak = VABSDIFF4 issue rate measured in this run "
                         "(tools/probe/probe.cu): one VABSDIFF4.U8.ACC per pair is the floor for a 3-byte vector; the ncu "
@@ -718,8 +720,8 @@ def extras(ctx, torch, dev, hbm_peak, peak_src):
         gbs = T3 * 12303 / (ms * 1e-3) / 1e9
         ex["c3_analysis"] = {"tiles": T3, "ms": ms, "tiles_per_s": T3 / (ms * 1e-3),
                              "roofline": {"kernel": "analyse_fast_kernel<64,1,1>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                                          "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                                          "bytes_per_tile": 12303}}
+                                          "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": measured_traffic("analyse_fast_kernel", 1),
+                                          "peak_source": peak_src, "bytes_per_tile": 12303}}
         del tiles, o1, o4
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
@@ -746,7 +748,7 @@ def extras(ctx, torch, dev, hbm_peak, peak_src):
                          "matched_px_per_s": S5 * S5 / (m_ms * 1e-3),
                          "roofline": {"kernel": "compose_tint_kernel<0>", "bound": "hbm", "achieved": b5 / (c_ms * 1e-3) / 1e9,
                                       "peak": hbm_peak, "unit": "GB/s", "frac": b5 / (c_ms * 1e-3) / 1e9 / hbm_peak,
-                                      "traffic": None, "peak_source": peak_src}}
+                                      "traffic": measured_traffic("compose_tint_kernel", 1), "peak_source": peak_src}}
         del tiles5, src5, out5
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001

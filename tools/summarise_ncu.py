@@ -2,6 +2,8 @@
 """Summarise ncu artefacts (read here, on the CPU box) into profiles/.
   python tools/summarise_ncu.py launches gpurun_out/launches.csv         -> per-kernel launch list
   python tools/summarise_ncu.py report gpurun_out/prof_X.ncu-rep         -> key metrics of a --set full capture
+  python tools/summarise_ncu.py traffic name=gpurun_out/prof_X.ncu-rep ... -> profiles/traffic.json: DRAM bytes of one launch per
+                                                                             named kernel + the commit, read by bench.py
 """
 import collections
 import csv
@@ -69,5 +71,40 @@ def report(path):
         print()
 
 
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+TIME = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}
+
+
+def traffic(pairs):
+    """name=report pairs -> profiles/traffic.json {commit, kernels: {name: {dram_bytes, dram_read, dram_write, ncu_us, kernel, report}}}"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    commit = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    out = {"commit": commit, "source": "ncu --set full --clock-control none, one launch each (tools/profile_r02.sh)", "kernels": {}}
+    for pair in pairs:
+        name, path = pair.split("=", 1)
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        if len(rows) < 3:
+            print(f"{name}: no data in {path}")
+            continue
+        hdr, units, vals = rows[0], rows[1], rows[2]
+
+        def get(metric, table):
+            i = hdr.index(metric)
+            return float(vals[i].replace(",", "")) * table[units[i]]
+
+        rd, wr = get("dram__bytes_read.sum", UNIT), get("dram__bytes_write.sum", UNIT)
+        out["kernels"][name] = {"dram_bytes": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
+                                "ncu_us": get("gpu__time_duration.sum", TIME), "kernel": vals[hdr.index("Kernel Name")],
+                                "report": os.path.basename(path)}
+        print(name, out["kernels"][name])
+    json.dump(out, open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
+    else:
+        {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
