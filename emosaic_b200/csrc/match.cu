@@ -246,6 +246,17 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
+    // Split mode (several CTAs share a query tile): publish (distance, window) and leave the search inside the window to
+    // match_finalize_window_kernel — a CTA that scans a short candidate range would otherwise spend most of its life in the
+    // latency-bound rescan below.  Windows are disjoint index ranges, so the 64-bit minimum is still (distance, smallest index).
+    if (p.keys) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t qi = qbase + r * NT + tid;
+            if (qi < p.Q) atomicMin(&p.keys[qi], ((unsigned long long)bestd[r] << 32) | idx[r]);
+        }
+        return;
+    }
     // Epilogue: the winner is the FIRST candidate of the remembered window that reaches the minimum
     // (candidates are scanned in rank order, so this is the canonical smallest-rank tie-break).
     // The window is re-read from global memory (L2-resident) with batched 128-bit loads.
@@ -291,14 +302,10 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
     for (int r = 0; r < R; r++) {
         const uint32_t qi = qbase + r * NT + tid;
         if (qi >= p.Q) continue;
-        if (p.keys) {
-            atomicMin(&p.keys[qi], ((unsigned long long)bestd[r] << 32) | idx[r]);
-        } else {
-            const uint32_t cnd = idx[r];
-            const int32_t t1 = (int32_t)(p.mirrored ? (cnd >> 1) : cnd) + 1;
-            p.item[qi] = (p.mirrored && (cnd & 1)) ? -t1 : t1;
-            p.dist[qi] = bestd[r];
-        }
+        const uint32_t cnd = idx[r];
+        const int32_t t1 = (int32_t)(p.mirrored ? (cnd >> 1) : cnd) + 1;
+        p.item[qi] = (p.mirrored && (cnd & 1)) ? -t1 : t1;
+        p.dist[qi] = bestd[r];
     }
 }
 
@@ -307,6 +314,7 @@ __global__ void match_init_keys_kernel(unsigned long long *keys, uint32_t Q) {
     if (i < Q) keys[i] = ~0ull;
 }
 
+// keys[q] = distance << 32 | candidate (the wide kernel's splits merge exact candidates)
 __global__ void match_finalize_kernel(const unsigned long long *__restrict__ keys, uint32_t Q, uint32_t mirrored,
                                       int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,24 +326,73 @@ __global__ void match_finalize_kernel(const unsigned long long *__restrict__ key
     dist[i] = (uint32_t)(k >> 32);
 }
 
+// Split mode, second half: keys[q] = distance << 32 | first candidate of the window that holds the winner.  One warp per
+// query: lane l takes candidates 4l .. 4l + 3 of the window (WIN = 128 = 32 lanes x 4), the first lane / candidate whose distance
+// equals the minimum is the canonical winner (smallest rank).  Coalesced, no dependent chain: microseconds for a whole stripe.
+template <int WORDS>
+__global__ void __launch_bounds__(256) match_finalize_window_kernel(const MatchParams p) {
+    static_assert(MATCH_WIN == 128, "one lane per 4 candidates");
+    const uint32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (qi >= p.Q) return;
+    const unsigned long long k = p.keys[qi];
+    const uint32_t best = (uint32_t)(k >> 32), w0 = (uint32_t)k;
+    uint32_t q[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) q[w] = 0;
+    const uint32_t by = qi / p.bw, bx = qi % p.bw, D = 3 * p.dim * p.dim;
+#pragma unroll
+    for (int b = 0; b < 4 * WORDS; b++) {
+        if ((uint32_t)b < D) {
+            const uint32_t cell = b / 3, ch = b % 3;
+            const uint32_t cy = cell / p.dim, cx = cell - cy * p.dim;
+            const uint32_t v = p.src[((size_t)(by * p.dim + cy) * p.W + (bx * p.dim + cx)) * 3 + ch];
+            q[b >> 2] |= v << (8 * (b & 3));
+        }
+    }
+    const uint4 *wc = reinterpret_cast<const uint4 *>(p.cand + ((size_t)w0 + 4 * lane) * WORDS);
+    uint32_t cw[4 * WORDS];
+#pragma unroll
+    for (int v = 0; v < WORDS; v++) {
+        const uint4 t4 = __ldg(wc + v);
+        cw[4 * v + 0] = t4.x; cw[4 * v + 1] = t4.y; cw[4 * v + 2] = t4.z; cw[4 * v + 3] = t4.w;
+    }
+    uint32_t found = 4;
+    if (sad_vec<WORDS, 3 * WORDS>(q, cw, 0u) == best) found = 3;
+    if (sad_vec<WORDS, 2 * WORDS>(q, cw, 0u) == best) found = 2;
+    if (sad_vec<WORDS, 1 * WORDS>(q, cw, 0u) == best) found = 1;
+    if (sad_vec<WORDS, 0 * WORDS>(q, cw, 0u) == best) found = 0;
+    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, found < 4);
+    const uint32_t first = hit ? (uint32_t)__ffs((int)hit) - 1 : 0;  // hit != 0: the window was chosen because it reaches `best`
+    const uint32_t pos = __shfl_sync(0xFFFFFFFFu, found, first);
+    if (lane == 0) {
+        const uint32_t cnd = w0 + 4 * first + (pos < 4 ? pos : 0);
+        const int32_t t1 = (int32_t)(p.mirrored ? (cnd >> 1) : cnd) + 1;
+        p.item[qi] = (p.mirrored && (cnd & 1)) ? -t1 : t1;
+        p.dist[qi] = best;
+    }
+}
+
 template <int WORDS, int R, int NT, int WIN = MATCH_WIN, int MINB = 0, int UNR = MATCH_UNROLL>
 static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     auto kern = match_kernel<WORDS, R, NT, WIN, MINB, UNR>;
     const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8;
     EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
-    // Split the candidate range across gridDim.y only when the query tiles cannot fill ~3 waves of resident
-    // CTAs, and never below ~16k candidates per CTA: every CTA pays a fixed prologue (query gather, pipeline
-    // fill) and epilogue (window rescan, merge), measured with tools/sweep_match.py.
+    // Split the candidate range across gridDim.y when the query tiles cannot fill the resident CTA slots: a split CTA pays a
+    // prologue (query gather, pipeline fill) but no epilogue any more (match_finalize_window_kernel), so short ranges are fine:
+    // at least 4 stages of candidates per CTA.
     int occ = 1;
     EMO_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT + 32, smem));
     if (occ < 1) occ = 1;
     const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)occ;
     uint32_t splits = 1;
-    if (qtiles < 3 * slots) {
-        const uint32_t by_fill = (3 * slots + qtiles - 1) / qtiles;
-        static const uint32_t min_len = getenv("EMO_MATCH_MINLEN") ? (uint32_t)atoi(getenv("EMO_MATCH_MINLEN")) : 16384u;  // tuning override
-        const uint32_t by_len = (p.n_chunks * p.chunk) / (WORDS == 1 ? 16384u : min_len);
+    // Measured on C2's row stripes (tools/sweep_match3.py, MINLENS=0): 64 block rows 204 -> 172 us, 32 rows 204 -> 104 us with
+    // 1.5 x the slots as the target; splitting a grid that already fills the slots costs 8 % (1178 vs 1086 us at 512 rows).
+    static const uint32_t fill_num = getenv("EMO_MATCH_FILL") ? (uint32_t)atoi(getenv("EMO_MATCH_FILL")) : 150u;  // tuning: % of the slots
+    if (qtiles < slots) {
+        const uint32_t by_fill = (fill_num * slots / 100u + qtiles - 1) / qtiles;
+        static const uint32_t min_len = getenv("EMO_MATCH_MINLEN") ? (uint32_t)atoi(getenv("EMO_MATCH_MINLEN")) : 0u;  // tuning override
+        const uint32_t by_len = min_len ? (p.n_chunks * p.chunk) / min_len : p.n_chunks / 4;
         splits = by_fill < by_len ? by_fill : by_len;
         if (splits < 1) splits = 1;
         if (splits > p.n_chunks) splits = p.n_chunks;
@@ -359,7 +416,7 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     kern<<<grid, NT + 32, smem, ctx->stream>>>(p);
     EMO_LAUNCH_CHECK(ctx);
     if (splits > 1) {
-        match_finalize_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, p.mirrored, p.item, p.dist);
+        match_finalize_window_kernel<WORDS><<<(Q + 7) / 8, 256, 0, ctx->stream>>>(p);
         EMO_LAUNCH_CHECK(ctx);
     }
     return EMO_OK;

@@ -35,7 +35,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "one":
 
 base = None
 for shape in os.environ.get("SHAPES", "2128,1,2,3,4,5,6,7").split(","):
-    for minlen in os.environ.get("MINLENS", "16384").split(","):
+    for minlen in os.environ.get("MINLENS", "0").split(","):
         env = dict(os.environ, EMO_MATCH_SHAPE3=shape, EMO_MATCH_MINLEN=minlen)
         r = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
         try:
