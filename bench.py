@@ -396,7 +396,7 @@ def run_ours(args):
         barrier()
         t_all, lead = None, 4.0
         for attempt in range(2):
-            box = [time.time_ns() + int(lead * 1e9) if rank == 0 else None]
+            box = [(time.time_ns() + int(lead * 1e9) if world > 1 else 0) if rank == 0 else None]   # one rank: nothing to wait for
             if world > 1:
                 dist.broadcast_object_list(box, src=0)
             ok = 1.0
