@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) match_index_kernel(const uint8_t *__restr
 // and dist = |dr| + |dg| + |db| in one VABSDIFF4 (the fourth byte of both words is zero).  The second gather goes to an
 // array of at most 512 KB that lives in L1 / L2: measured free next to the table gather (a shared-memory copy of the
 // colours was tried and bought nothing: 107 vs 105 us at 30 000 tiles with one 1024-thread CTA per SM, 93 vs 93 us at 4096).
-template <int MODE, int GROUPS>  // GROUPS x 4 pixels per thread and iteration, all their loads in flight together
+template <int MODE>
 __global__ void __launch_bounds__(256)
     match_index16_kernel(const uint8_t *__restrict__ src, const uint16_t *__restrict__ lut16, const uint32_t *__restrict__ colors,
                          const uint2 *__restrict__ entry, uint32_t Q, int32_t *__restrict__ item, uint32_t *__restrict__ dist) {
@@ -272,49 +272,32 @@ __global__ void __launch_bounds__(256)
     const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
     // (an explicit griddepcontrol.launch_dependents at this point was measured: 79.8 vs 79.0 us per 512-row step — nothing to gain)
     grid_dependency_wait();  // everything below may depend on the previous kernel of the stream (index build, item map readers)
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t g0 = blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += stride * GROUPS) {
-        uint32_t c[GROUPS][4], sl[GROUPS][4];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const uint32_t q0 = g << 2;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (size_t)g * 3;
+        const uint32_t w0 = ldg_nc_hint_u32(w, drop), w1 = ldg_nc_hint_u32(w + 1, drop), w2 = ldg_nc_hint_u32(w + 2, drop);
+        uint32_t c[4], sl[4], it[4], d[4];
+        c[0] = w0 & 0xFFFFFFu;
+        c[1] = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
+        c[2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
+        c[3] = w2 >> 8;
 #pragma unroll
-        for (int u = 0; u < GROUPS; u++) {  // consecutive threads keep consecutive groups: coalesced in every round
-            const uint32_t g = g0 + u * stride;
-            if (g < groups) {
-                const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + (size_t)g * 3;
-                const uint32_t w0 = ldg_nc_hint_u32(w, drop), w1 = ldg_nc_hint_u32(w + 1, drop), w2 = ldg_nc_hint_u32(w + 2, drop);
-                c[u][0] = w0 & 0xFFFFFFu;
-                c[u][1] = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
-                c[u][2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
-                c[u][3] = w2 >> 8;
+        for (int m = 0; m < 4; m++) sl[m] = ldg_nc_hint_u16(lut16 + c[m], keep);
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            uint32_t col;
+            if (MODE == 1) {
+                col = __ldg(colors + sl[m]) & 0xFFFFFFu;
+                it[m] = sl[m] + 1;
             } else {
-                c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0;
+                const uint2 e = __ldg(entry + sl[m]);
+                col = e.y;
+                it[m] = e.x + 1;
             }
+            d[m] = sad4(c[m], col, 0);
         }
-#pragma unroll
-        for (int u = 0; u < GROUPS; u++)
-#pragma unroll
-            for (int m = 0; m < 4; m++) sl[u][m] = ldg_nc_hint_u16(lut16 + c[u][m], keep);
-#pragma unroll
-        for (int u = 0; u < GROUPS; u++) {
-            const uint32_t g = g0 + u * stride;
-            uint32_t it[4], d[4];
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-                uint32_t col;
-                if (MODE == 1) {
-                    col = __ldg(colors + sl[u][m]) & 0xFFFFFFu;
-                    it[m] = sl[u][m] + 1;
-                } else {
-                    const uint2 e = __ldg(entry + sl[u][m]);
-                    col = e.y;
-                    it[m] = e.x + 1;
-                }
-                d[m] = sad4(c[u][m], col, 0);
-            }
-            if (g < groups) {
-                *reinterpret_cast<uint4 *>(item + (g << 2)) = make_uint4(it[0], it[1], it[2], it[3]);  // compose's input: kept in L2
-                stg_hint_v4(dist + (g << 2), make_uint4(d[0], d[1], d[2], d[3]), drop);                // nothing on the device reads dist again
-            }
-        }
+        *reinterpret_cast<uint4 *>(item + q0) = make_uint4(it[0], it[1], it[2], it[3]);  // compose's input: kept in L2
+        stg_hint_v4(dist + q0, make_uint4(d[0], d[1], d[2], d[3]), drop);                // nothing on the device reads dist again
     }
 }
 
@@ -324,7 +307,7 @@ static int launch_index16(emo_ctx *ctx, const uint8_t *src, uint32_t Q4, int32_t
     // (two groups per thread, all loads in flight together, were measured: 20.0 vs 20.7 us on a 512-row stripe, 98.6 vs 98.0 us
     // on the whole image — the gather is not limited by per-thread parallelism; one group kept)
     const uint32_t blocks = min((groups + 255) / 256, (uint32_t)ctx->sm_count * 8 * 4);
-    EMO_CK(emo_launch_pdl(match_index16_kernel<MODE, 1>, dim3(blocks), dim3(256), 0, ctx->stream, src, (const uint16_t *)ctx->lut16,
+    EMO_CK(emo_launch_pdl(match_index16_kernel<MODE>, dim3(blocks), dim3(256), 0, ctx->stream, src, (const uint16_t *)ctx->lut16,
                           (const uint32_t *)ctx->cand, (const uint2 *)ctx->idx_entry, Q4, item, dist));
     EMO_LAUNCH_CHECK(ctx);
     return EMO_OK;

@@ -108,7 +108,9 @@ struct MatchParams {
     const uint32_t *cand;   // [n_chunks*chunk][WORDS]
     uint32_t chunk;         // candidates per stage (multiple of MATCH_WIN)
     uint32_t n_chunks;      // total stages in the candidate array
-    uint32_t chunks_per_split;
+    uint32_t chunks_per_split;  // stages per split CTA
+    uint32_t split_ctas;        // the first split_ctas CTAs of the grid share query tiles: tile = split_tile0 + x / splits, part = x % splits
+    uint32_t splits, split_tile0;
     const uint8_t *src;     // [H][W][3]
     uint32_t W, bw, Q, dim;
     uint32_t mirrored;      // 1: candidate c -> tile c>>1, flipped c&1 ; 0: candidate c -> tile c
@@ -153,8 +155,13 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
     }
     __syncthreads();
 
-    const uint32_t c0 = blockIdx.y * p.chunks_per_split;
-    const uint32_t c1 = min(c0 + p.chunks_per_split, p.n_chunks);
+    // Grid = [split CTAs | whole-range CTAs].  A split CTA scans one part of the candidate range for a query tile it shares with
+    // `splits - 1` others and publishes (distance, window); a whole-range CTA owns its tile and finishes it itself.  The split
+    // CTAs come first so that they run next to the long ones instead of after them.
+    const bool split = blockIdx.x < p.split_ctas;
+    const uint32_t tile = split ? p.split_tile0 + blockIdx.x / p.splits : blockIdx.x - p.split_ctas;
+    const uint32_t c0 = split ? (blockIdx.x % p.splits) * p.chunks_per_split : 0u;
+    const uint32_t c1 = split ? min(c0 + p.chunks_per_split, p.n_chunks) : p.n_chunks;
 
     if (warp == CONSUMER_WARPS) {
         // ---- producer warp: one lane streams candidate stages through the ring with TMA bulk copies
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
     // and one VIMNMX3.U16x2 folds four candidates into best2.  ALU pipe: 1.25 instr/pair, FMA pipe: 0.5.
     // Distances are < 65536 because 255 * 3N <= 12240 for the supported N.
     uint32_t q[R][WORDS], best2[R], seen2[R], bestd[R], idx[R];
-    const uint32_t qbase = blockIdx.x * (uint32_t)(NT * R);
+    const uint32_t qbase = tile * (uint32_t)(NT * R);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         uint32_t qi = qbase + r * NT + tid;
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
     // Split mode (several CTAs share a query tile): publish (distance, window) and leave the search inside the window to
     // match_finalize_window_kernel — a CTA that scans a short candidate range would otherwise spend most of its life in the
     // latency-bound rescan below.  Windows are disjoint index ranges, so the 64-bit minimum is still (distance, smallest index).
-    if (p.keys) {
+    if (split) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const uint32_t qi = qbase + r * NT + tid;
@@ -309,8 +316,8 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
     }
 }
 
-__global__ void match_init_keys_kernel(unsigned long long *keys, uint32_t Q) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void match_init_keys_kernel(unsigned long long *keys, uint32_t Q, uint32_t q_begin = 0) {
+    const uint32_t i = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < Q) keys[i] = ~0ull;
 }
 
@@ -330,9 +337,9 @@ __global__ void match_finalize_kernel(const unsigned long long *__restrict__ key
 // query: lane l takes candidates 4l .. 4l + 3 of the window (WIN = 128 = 32 lanes x 4), the first lane / candidate whose distance
 // equals the minimum is the canonical winner (smallest rank).  Coalesced, no dependent chain: microseconds for a whole stripe.
 template <int WORDS>
-__global__ void __launch_bounds__(256) match_finalize_window_kernel(const MatchParams p) {
+__global__ void __launch_bounds__(256) match_finalize_window_kernel(const MatchParams p, uint32_t q_begin) {
     static_assert(MATCH_WIN == 128, "one lane per 4 candidates");
-    const uint32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t qi = q_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (qi >= p.Q) return;
     const unsigned long long k = p.keys[qi];
     const uint32_t best = (uint32_t)(k >> 32), w0 = (uint32_t)k;
@@ -385,38 +392,56 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     EMO_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT + 32, smem));
     if (occ < 1) occ = 1;
     const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)occ;
-    uint32_t splits = 1;
-    // Measured on C2's row stripes (tools/sweep_match3.py, MINLENS=0): 64 block rows 204 -> 172 us, 32 rows 204 -> 104 us with
-    // 1.5 x the slots as the target; splitting a grid that already fills the slots costs 8 % (1178 vs 1086 us at 512 rows).
+    // Which query tiles share their candidate range between several CTAs:
+    //  - fewer tiles than resident slots: all of them, enough parts for 1.5 x the slots (C2's row stripes, tools/sweep_match3.py,
+    //    MINLENS=0: 64 block rows 204 -> 172 us, 32 rows 204 -> 104 us; splitting a grid that already fills the slots costs 8 %);
+    //  - a small ragged last wave (rem = tiles % slots <= slots / 8): only those rem tiles, slots / rem parts each, so that the
+    //    remainder fills the machine next to the whole-range CTAs instead of running one CTA per SM after them.  Without it the
+    //    time is a staircase — 888 tiles 954 us, anything from 889 to 1024 tiles 1105 us on C2's library — with it 896 tiles take
+    //    978 us, 912: 1008, 960: 1060, 992: 1090; from rem ~ 120 on the lone CTAs are as cheap (1024 tiles: 1139 vs 1105 us).
+    // A part is at least 4 stages long.
+    uint32_t splits = 1, split_tiles = 0;
+    const uint32_t max_parts = p.n_chunks / 4;
     static const uint32_t fill_num = getenv("EMO_MATCH_FILL") ? (uint32_t)atoi(getenv("EMO_MATCH_FILL")) : 150u;  // tuning: % of the slots
+    static const bool tail_on = !(getenv("EMO_MATCH_TAIL") && atoi(getenv("EMO_MATCH_TAIL")) == 0);            // tuning / A-B switch
     if (qtiles < slots) {
         const uint32_t by_fill = (fill_num * slots / 100u + qtiles - 1) / qtiles;
         static const uint32_t min_len = getenv("EMO_MATCH_MINLEN") ? (uint32_t)atoi(getenv("EMO_MATCH_MINLEN")) : 0u;  // tuning override
-        const uint32_t by_len = min_len ? (p.n_chunks * p.chunk) / min_len : p.n_chunks / 4;
+        const uint32_t by_len = min_len ? (p.n_chunks * p.chunk) / min_len : max_parts;
         splits = by_fill < by_len ? by_fill : by_len;
-        if (splits < 1) splits = 1;
-        if (splits > p.n_chunks) splits = p.n_chunks;
+        split_tiles = qtiles;
+    } else if (tail_on) {
+        const uint32_t rem = qtiles % slots;
+        if (rem && 8 * rem <= slots) {
+            splits = slots / rem < max_parts ? slots / rem : max_parts;
+            split_tiles = rem;
+        }
     }
-    if (const char *e = getenv("EMO_MATCH_SPLITS")) {  // tuning override
+    if (const char *e = getenv("EMO_MATCH_SPLITS")) {  // tuning override: every tile in that many parts
         const int v = atoi(e);
-        if (v >= 1) splits = (uint32_t)v < p.n_chunks ? (uint32_t)v : p.n_chunks;
+        if (v >= 1) { splits = (uint32_t)v < p.n_chunks ? (uint32_t)v : p.n_chunks; split_tiles = qtiles; }
     }
+    if (splits < 2) { splits = 1; split_tiles = 0; }
     p.chunks_per_split = (p.n_chunks + splits - 1) / splits;
-    splits = (p.n_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
-    if (splits > 1) {
+    splits = (p.n_chunks + p.chunks_per_split - 1) / p.chunks_per_split;  // every part non-empty
+    if (splits < 2) { splits = 1; split_tiles = 0; }
+    p.splits = splits;
+    p.split_tile0 = qtiles - split_tiles;
+    p.split_ctas = split_tiles * splits;
+    const uint32_t q_begin = p.split_tile0 * (uint32_t)(NT * R);  // queries from here on are merged through the keys
+    if (split_tiles) {
         int rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, (size_t)Q * 8);
         if (rc) return rc;
         p.keys = ctx->keys;
-        match_init_keys_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q);
+        match_init_keys_kernel<<<(Q - q_begin + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, q_begin);
         EMO_LAUNCH_CHECK(ctx);
     } else {
         p.keys = nullptr;
     }
-    dim3 grid(qtiles, splits);
-    kern<<<grid, NT + 32, smem, ctx->stream>>>(p);
+    kern<<<p.split_ctas + p.split_tile0, NT + 32, smem, ctx->stream>>>(p);
     EMO_LAUNCH_CHECK(ctx);
-    if (splits > 1) {
-        match_finalize_window_kernel<WORDS><<<(Q + 7) / 8, 256, 0, ctx->stream>>>(p);
+    if (split_tiles) {
+        match_finalize_window_kernel<WORDS><<<(Q - q_begin + 7) / 8, 256, 0, ctx->stream>>>(p, q_begin);
         EMO_LAUNCH_CHECK(ctx);
     }
     return EMO_OK;
@@ -629,6 +654,7 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
     p.chunk = ctx->chunk;
     p.n_chunks = ctx->n_chunks;
     p.chunks_per_split = ctx->n_chunks;
+    p.split_ctas = 0; p.splits = 1; p.split_tile0 = 0;
     p.src = src;
     p.W = W;
     p.dim = ctx->dim;
