@@ -67,6 +67,9 @@ def deserialize_tile_set(buf: bytes, N: int, extensions: Optional[Iterable[str]]
         return b
 
     (T,) = struct.unpack("<Q", take(8))
+    # every tile costs at least 8 + 3N + 3 bytes here and 8 more in the path list: a corrupt count fails before any allocation
+    if T > (len(mv) - pos) // (3 * N + 19):
+        raise ValueError("truncated cache file")
     colors = np.zeros((T, N, 3), np.uint8)
     dates: List[Optional[str]] = []
     for t in range(T):

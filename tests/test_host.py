@@ -167,3 +167,26 @@ def test_cache_golden_bytes():
     # hand-decoded header: 5 tiles, 12 colour bytes each
     assert blob[:8] == (5).to_bytes(8, "little") and blob[8:16] == (12).to_bytes(8, "little")
     assert len(blob) == 8 + 5 * (8 + 12 + 2 + 1) + 2 * (8 + 10) + 8 + sum(8 + len(x.encode()) for x in paths)
+
+
+def test_cache_corrupt_lengths_fail_fast():
+    """A cache file with absurd length fields (tile count, date length, path length) is rejected with ValueError before any
+    allocation or out-of-range read — the reference's bincode returns Err and the tile set is re-analysed (main.rs:617-623)."""
+    import struct
+    from emosaic_b200 import cache
+    colors = np.arange(6, dtype=np.uint8).reshape(2, 1, 3)
+    blob = bytearray(cache.serialize_tile_set(colors, ["/tmp/a.jpg", "/tmp/b.jpg"], ["2020:01:01", None]))
+    ok = cache.deserialize_tile_set(bytes(blob), 1)
+    assert ok[1] == ["/tmp/a.jpg", "/tmp/b.jpg"] and ok[2] == ["2020:01:01", None]
+    huge = struct.pack("<Q", 0xFFFFFFFFFFFFFFFF)
+    for off in (0,                      # tile count
+                8 + 8 + 3 + 2 + 1,      # length of the first date string
+                len(blob) - 10 - 8):    # length of the last path
+        bad = bytearray(blob)
+        bad[off:off + 8] = huge
+        with pytest.raises(ValueError):
+            cache.deserialize_tile_set(bytes(bad), 1)
+    with pytest.raises(ValueError):
+        cache.deserialize_tile_set(bytes(blob[:-3]), 1)
+    with pytest.raises(ValueError):
+        cache.deserialize_tile_set(bytes(blob), 4)      # wrong vector length for this mode
