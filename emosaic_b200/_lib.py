@@ -17,7 +17,7 @@ EXPORTS = [
     "emo_host_alloc", "emo_host_free", "emo_copy_h2d", "emo_copy_d2h", "emo_analyse", "emo_analyse_dev",
     "emo_analyse_fused", "emo_analyse_fused_dev", "emo_set_library", "emo_set_library_dev", "emo_library_info", "emo_build_index",
     "emo_set_match_mode", "emo_match", "emo_topk", "emo_topk_dev", "emo_no_repeat",
-    "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev", "emo_stats", "emo_stats_dev",
+    "emo_match_dev", "emo_compose", "emo_compose_dev", "emo_compose_overlay", "emo_compose_overlay_dev", "emo_mosaic", "emo_mosaic_dev", "emo_reserve", "emo_stats", "emo_stats_dev",
     "emo_resize", "emo_resize_dev", "emo_resize_taps",
     "emo_stripe_bounds", "emo_host_register", "emo_host_unregister",
     "emo_comm_unique_id", "emo_comm_init_rank", "emo_comm_info", "emo_comm_set_library", "emo_comm_set_library_dev",
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
         "emo_compose_overlay_dev": (C.c_int, [vp, i32p, C.c_uint32, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint8, u8p]),
         "emo_mosaic": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
         "emo_mosaic_dev": (C.c_int, [vp, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, i32p, u32p, u8p]),
+        "emo_reserve": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32]),
         "emo_stats": (C.c_int, [vp, i32p, u32p, C.c_uint64, C.c_uint32, vp, u32p]),
         "emo_stats_dev": (C.c_int, [vp, i32p, u32p, C.c_uint64, C.c_uint32, vp, u32p]),
         "emo_resize": (C.c_int, [vp, u8p] + [C.c_uint32] * 9 + [u8p]),

@@ -348,6 +348,10 @@ class Context:
         check(self._lib.emo_compose_dev(self._h, C.c_void_p(item_dev), C.c_void_p(src_dev or 0), W, H, out_channels,
                                         tint_alpha, C.c_void_p(out_dev)))
 
+    def reserve(self, W: int, H: int, out_channels: int = 3):
+        """emo_reserve: size the staging buffers of the host-pointer calls for sources up to W x H ahead of time."""
+        check(self._lib.emo_reserve(self._h, W, H, out_channels))
+
     def stats(self, item, dist, want_usage: bool = True):
         """emo_stats: the reductions of RenderStats (stats.rs:87-139, :169-175) over a render's maps, on the GPU:
         {"placed", "total_distance", "max_distance"} and usage [T] (blocks per tile, either orientation)."""

@@ -133,6 +133,7 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
 int emo_launch_topk(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t first, uint32_t k, const uint8_t *exclude,
                     int32_t *item, uint32_t *dist);
 int emo_launch_build_index(emo_ctx *ctx);
+int emo_index_reserve(emo_ctx *ctx);  // allocates the index tables without building them
 int emo_prepare_match(emo_ctx *ctx, uint64_t queries);  // builds the 1to1 index when the mode / size rule asks for it
 bool emo_index_supported(const emo_ctx *ctx);
 int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t *item, uint32_t *dist);

@@ -685,6 +685,34 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
 
 }  // extern "C"
 
+// Block rows per pipeline step of emo_mosaic: ~64 MB of output (long enough copies to run at the PCIe rate, short enough that
+// the first and the last chunk — the parts of the pipeline that do not overlap — stay small), but at least ~1.2 M queries per
+// launch when that still leaves >= 8 chunks to overlap (launch-bound lookups / scans on small chunks); at least one block row.
+static uint32_t mosaic_rows_per_chunk(uint32_t bw, uint32_t bh, size_t row_out) {
+    uint32_t rows = (uint32_t)((64ull << 20) / (row_out ? row_out : 1));
+    const uint32_t rows_for_q = ((1200000u + bw - 1) / bw);
+    if (rows < rows_for_q && rows_for_q * 8 <= bh) rows = rows_for_q;
+    if (rows < 1) rows = 1;
+    if (rows > bh) rows = bh;
+    return rows;
+}
+
+extern "C" int emo_reserve(emo_ctx *ctx, uint32_t W, uint32_t H, uint32_t oc) {
+    EMO_REQUIRE(ctx, EMO_ERR_ARG, "emo_reserve: ctx is NULL");
+    EMO_REQUIRE(ctx->T > 0, EMO_ERR_STATE, "emo_reserve: no library set (the staging sizes depend on its cell grid and tile size)");
+    EMO_REQUIRE(W > 0 && H > 0 && (oc == 3 || oc == 4), EMO_ERR_ARG, "emo_reserve: bad geometry %ux%u, %u channels", W, H, oc);
+    EMO_CK(cudaSetDevice(ctx->device));
+    const uint32_t dim = ctx->dim, bw = (W + dim - 1) / dim, bh = (H + dim - 1) / dim;
+    const size_t Q = (size_t)bw * bh, row_out = (size_t)bw * ctx->ts * ctx->ts * oc;
+    int rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], (size_t)bw * dim * bh * dim * 3))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], Q * 4))) return rc;
+    if ((rc = emo_ensure(ctx, &ctx->stage[4], &ctx->stage_cap[4], Q * 4))) return rc;
+    if (ctx->has_px && (rc = emo_ensure(ctx, &ctx->stage[5], &ctx->stage_cap[5], row_out * mosaic_rows_per_chunk(bw, bh, row_out) * 2))) return rc;
+    if (emo_index_supported(ctx) && ctx->match_mode != EMO_MATCH_SCAN && (rc = emo_index_reserve(ctx))) return rc;  // 1to1: the 64 + 32 MiB tables
+    return EMO_OK;
+}
+
 // total_queries: the block count the 1to1 index rule is applied to (0 = this image's own); a multi-GPU caller passes the
 // whole image's count so that every stripe takes the same decision as a single-GPU run would.
 int emo_mosaic_host_impl(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_t oc, uint8_t tint_alpha, int32_t *item,
@@ -698,14 +726,7 @@ int emo_mosaic_host_impl(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t 
     const uint32_t dim = ctx->dim, ts = ctx->ts, bw = W / dim, bh = H / dim;
     const size_t Q = (size_t)bw * bh, sb = (size_t)W * H * 3;
     const size_t row_out = (size_t)bw * ts * ts * oc;  // output bytes per block row
-    // chunk: ~64 MB of output per step, but at least ~1.2 M queries (the match kernel needs that many to fill
-    // the GPU without splitting the candidate range) as long as that still leaves >= 8 chunks to overlap the
-    // D2H of one chunk with the kernels of the next; at least one block row
-    uint32_t rows_per_chunk = (uint32_t)((64ull << 20) / (row_out ? row_out : 1));
-    const uint32_t rows_for_q = ((1200000u + bw - 1) / bw);
-    if (rows_per_chunk < rows_for_q && rows_for_q * 8 <= bh) rows_per_chunk = rows_for_q;
-    if (rows_per_chunk < 1) rows_per_chunk = 1;
-    if (rows_per_chunk > bh) rows_per_chunk = bh;
+    const uint32_t rows_per_chunk = mosaic_rows_per_chunk(bw, bh, row_out);
     const size_t chunk_out = row_out * rows_per_chunk;
     if ((rc = emo_ensure(ctx, &ctx->stage[2], &ctx->stage_cap[2], sb))) return rc;
     if ((rc = emo_ensure(ctx, &ctx->stage[3], &ctx->stage_cap[3], Q * 4))) return rc;

@@ -159,6 +159,18 @@ __global__ void __launch_bounds__(256) index_compact_kernel(const uint32_t *__re
     *reinterpret_cast<uint4 *>(lut16 + i) = make_uint4(k[0] | k[1] << 16, k[2] | k[3] << 16, k[4] | k[5] << 16, k[6] | k[7] << 16);
 }
 
+// the tables of the index, allocated once per ctx (emo_reserve calls this ahead of the first match)
+int emo_index_reserve(emo_ctx *ctx) {
+    if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
+    if (!ctx->lut16) EMO_CK(cudaMalloc(&ctx->lut16, IDX_CELLS * sizeof(uint16_t)));
+    if (ctx->T > IDX16_SLOTS) {
+        int rc = emo_ensure(ctx, (void **)&ctx->idx_slot_of_tile, &ctx->idx_slot_cap, (size_t)ctx->T * 4);
+        if (rc) return rc;
+        if (!ctx->idx_entry) EMO_CK(cudaMalloc(&ctx->idx_entry, IDX16_SLOTS * sizeof(uint2) + 16));
+    }
+    return EMO_OK;
+}
+
 int emo_launch_build_index(emo_ctx *ctx) {
     if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
     EMO_CK(cudaMemsetAsync(ctx->lut, 0xFF, IDX_CELLS * sizeof(uint32_t), ctx->stream));

@@ -246,6 +246,10 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
                uint8_t tint_alpha, int32_t *item, uint32_t *dist, uint8_t *out);
 int emo_mosaic_dev(emo_ctx *ctx, const uint8_t *src_dev, uint32_t W, uint32_t H, uint32_t out_channels,
                    uint8_t tint_alpha, int32_t *item_dev, uint32_t *dist_dev, uint8_t *out_dev);
+/* The host-pointer calls stage through device buffers the ctx grows on demand (a synchronise + free + allocate the first
+ * time a larger image arrives).  emo_reserve sizes them ahead of time for sources up to W x H with the resident library
+ * (emo_match, emo_compose, emo_mosaic with out_channels 3 or 4), so that no call on the timed path allocates. */
+int emo_reserve(emo_ctx *ctx, uint32_t W, uint32_t H, uint32_t out_channels);
 
 /* ---- multi-GPU -----------------------------------------------------------------------------------
  * The path shards without an exchange step.  The units are the reference's own parallel tasks: one block row of

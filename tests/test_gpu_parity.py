@@ -592,3 +592,46 @@ def test_stats_reduction_on_the_gpu(ctx):
     bad = item.copy(); bad[0, 0] = T + 1
     with pytest.raises(emo.EmosaicError):
         ctx.stats(bad, dist)
+
+
+def test_reserve_presizes_the_staging_buffers(ctx):
+    """emo_reserve: after it, the host-pointer calls for images up to that size do not allocate (device memory in use does not
+    change across the first emo_mosaic), and results are what they were."""
+    import torch
+    rng = np.random.default_rng(31)
+    tiles = rng.integers(0, 256, (500, 8, 8, 3), dtype=np.uint8)
+    colors = oracle.analyse_tiles(tiles, 4)
+    c = emo.Context(0)
+    try:
+        c.set_library(colors, tiles)
+        with pytest.raises(emo.EmosaicError):
+            c.reserve(0, 10, 3)
+        c.reserve(640, 480, 4)
+        c.sync()
+        free0 = torch.cuda.mem_get_info(0)[0]
+        src = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+        out, item, dist = c.mosaic(src, 4, 127)
+        out3, _, _ = c.mosaic(src[:100, :200], 3, 0)
+        assert torch.cuda.mem_get_info(0)[0] == free0, "a staged call allocated after emo_reserve"
+        ri, rd = oracle.match(colors, src)
+        assert (item == ri).all() and (dist == rd).all()
+        assert (out == oracle.tint(oracle.render(tiles, ri), src, 127)).all()
+        # 1to1: the search index's tables are part of the reservation
+        c1 = oracle.analyse_tiles(tiles, 1)
+        c.set_library(c1, tiles)
+        c.set_match_mode("index")
+        c.reserve(256, 256, 3)
+        c.sync()
+        free1 = torch.cuda.mem_get_info(0)[0]
+        o1, i1, d1 = c.mosaic(src[:256, :256], 3, 0)
+        assert torch.cuda.mem_get_info(0)[0] == free1, "the first 1to1 match allocated after emo_reserve"
+        r1, rd1 = oracle.match(c1, src[:256, :256])
+        assert (i1 == r1).all() and (d1 == rd1).all()
+    finally:
+        c.close()
+    fresh = emo.Context(0)
+    try:
+        with pytest.raises(emo.EmosaicError):
+            fresh.reserve(64, 64, 3)          # no library yet
+    finally:
+        fresh.close()
