@@ -710,6 +710,8 @@ extern "C" int emo_reserve(emo_ctx *ctx, uint32_t W, uint32_t H, uint32_t oc) {
     if ((rc = emo_ensure(ctx, &ctx->stage[4], &ctx->stage_cap[4], Q * 4))) return rc;
     if (ctx->has_px && (rc = emo_ensure(ctx, &ctx->stage[5], &ctx->stage_cap[5], row_out * mosaic_rows_per_chunk(bw, bh, row_out) * 2))) return rc;
     if (emo_index_supported(ctx) && ctx->match_mode != EMO_MATCH_SCAN && (rc = emo_index_reserve(ctx))) return rc;  // 1to1: the 64 + 32 MiB tables
+    if (!ctx->wide && (rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, Q * 8))) return rc;  // merge keys of a split scan
+    if (oc == 4 && ctx->tint.alpha < 0 && (rc = emo_prepare_tint(ctx, 127))) return rc;              // the blend tables (rebuilt per alpha, allocated once)
     return EMO_OK;
 }
 
