@@ -635,3 +635,20 @@ def test_reserve_presizes_the_staging_buffers(ctx):
             fresh.reserve(64, 64, 3)          # no library yet
     finally:
         fresh.close()
+
+
+@pytest.mark.parametrize("N,T,H,W", [(4, 4000, 2 * 449, 2 * 512), (4, 4000, 2 * 460, 2 * 512), (1, 20000, 300, 2048 + 40), (9, 2500, 3 * 150, 3 * 768)])
+def test_scan_with_a_ragged_last_wave(ctx, N, T, H, W):
+    """Query-tile counts just above a whole number of resident CTA waves: the remainder tiles are dealt out in parts (split CTAs +
+    whole-range CTAs in one grid, merged through the (distance, window) keys).  Oracle parity on the whole map."""
+    rng = np.random.default_rng(N * T)
+    colors = (rng.integers(0, 256, (T, N, 3)) // 8 * 8).astype(np.uint8)      # coarse colours: ties across the part boundaries
+    src = (rng.integers(0, 256, (H, W, 3)) // 4 * 4).astype(np.uint8)
+    ctx.set_library(colors)
+    ctx.set_match_mode("scan")
+    try:
+        item, dist = ctx.match(src)
+    finally:
+        ctx.set_match_mode("auto")
+    ri, rd = oracle.KdTree(colors).match(src)
+    assert (dist == rd).all() and (item == ri).all()
