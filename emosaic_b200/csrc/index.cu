@@ -144,7 +144,15 @@ __global__ void index_winners_kernel(const uint32_t *__restrict__ cand, uint32_t
     }
 }
 
-// lut16[cell] = slot of the cell's winner; 8 cells per thread.  DIRECT: slot = tile index.
+// Position of a colour in the compact table: blocked, 4 x 4 x 4 colours per 128-byte line (64 u16) — the pixels of a photograph
+// differ from their neighbours by a few levels in EVERY channel, so a line that spans 64 levels of r at fixed (g, b) is shared by
+// far fewer lanes of a warp than a line that spans 4 levels of each; a uniformly random source does not care.
+__host__ __device__ __forceinline__ uint32_t idx16_pos(uint32_t c) {  // c = r | g << 8 | b << 16
+    const uint32_t blk = ((c >> 2) & 63u) | ((c >> 10) & 63u) << 6 | ((c >> 18) & 63u) << 12;
+    return blk << 6 | (c & 3u) | ((c >> 8) & 3u) << 2 | ((c >> 16) & 3u) << 4;
+}
+
+// lut16[idx16_pos(cell)] = slot of the cell's winner; 8 cells (two runs of 4 along r) per thread.  DIRECT: slot = tile index.
 template <bool DIRECT>
 __global__ void __launch_bounds__(256) index_compact_kernel(const uint32_t *__restrict__ lut, const uint32_t *__restrict__ slot_of_tile,
                                                             uint16_t *__restrict__ lut16) {
@@ -156,7 +164,9 @@ __global__ void __launch_bounds__(256) index_compact_kernel(const uint32_t *__re
         k[m] &= IDX_TILE_MASK;
         if (!DIRECT) k[m] = __ldg(slot_of_tile + k[m]);
     }
-    *reinterpret_cast<uint4 *>(lut16 + i) = make_uint4(k[0] | k[1] << 16, k[2] | k[3] << 16, k[4] | k[5] << 16, k[6] | k[7] << 16);
+    // cells i .. i+3 and i+4 .. i+7 are the r-runs of two neighbouring blocks: 8 bytes each, 8-byte aligned
+    *reinterpret_cast<uint2 *>(lut16 + idx16_pos((uint32_t)i)) = make_uint2(k[0] | k[1] << 16, k[2] | k[3] << 16);
+    *reinterpret_cast<uint2 *>(lut16 + idx16_pos((uint32_t)i + 4)) = make_uint2(k[4] | k[5] << 16, k[6] | k[7] << 16);
 }
 
 // the tables of the index, allocated once per ctx (emo_reserve calls this ahead of the first match)
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(256)
         c[2] = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
         c[3] = w2 >> 8;
 #pragma unroll
-        for (int m = 0; m < 4; m++) sl[m] = ldg_nc_hint_u16(lut16 + c[m], keep);
+        for (int m = 0; m < 4; m++) sl[m] = ldg_nc_hint_u16(lut16 + idx16_pos(c[m]), keep);
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             uint32_t col;

@@ -11,7 +11,14 @@ MODE = os.environ.get("MODE", "auto")   # auto | index_wide | index_compact
 ctx = emo.Context(0)
 dev = torch.device("cuda", 0)
 tiles = torch.from_numpy(np.random.default_rng(1234).integers(0, 256, (T * ts * ts * 3,), dtype=np.uint8)).to(dev)
-src = torch.from_numpy(np.random.default_rng(5678).integers(0, 256, (H * W * 3,), dtype=np.uint8)).to(dev)
+if os.environ.get("SRC", "uniform").startswith("photo"):   # SRC=photo:<noise>: smooth RGB gradient + uniform noise of +-<noise> per channel
+    noise = int(os.environ["SRC"].split(":")[1]) if ":" in os.environ["SRC"] else 6
+    yy, xx = np.mgrid[0:H, 0:W]
+    ph = np.stack([xx * 255 // (W - 1), yy * 255 // (H - 1), (xx + yy) * 255 // (W + H - 2)], -1)
+    ph = np.clip(ph + np.random.default_rng(99).integers(-noise, noise + 1, ph.shape), 0, 255).astype(np.uint8)
+    src = torch.from_numpy(ph.reshape(-1)).to(dev)
+else:
+    src = torch.from_numpy(np.random.default_rng(5678).integers(0, 256, (H * W * 3,), dtype=np.uint8)).to(dev)
 colors = torch.empty(T * 3, dtype=torch.uint8, device=dev)
 item = torch.empty(H * W, dtype=torch.int32, device=dev); dist = torch.empty(H * W, dtype=torch.int32, device=dev)
 out = torch.empty(H * ts * W * ts * 3, dtype=torch.uint8, device=dev)
@@ -44,5 +51,5 @@ for n in ([int(x) for x in os.environ['NS'].split(',')] if os.environ.get('NS') 
     else:
         m = np.mean([ctx.mark_elapsed(3 * k, 3 * k + 1) for k in range(K)]); c = np.mean([ctx.mark_elapsed(3 * k + 1, 3 * k + 2) for k in range(K)])
     base = base or ms
-    print(f"T={T} mode={MODE} fused={int(fused)} rows={Hs:5d} (N={n}): step {ms*1e3:7.1f} us  match {m*1e3:6.1f} us  compose {c*1e3:6.1f} us  "
+    print(f"src={os.environ.get('SRC', 'uniform')} T={T} mode={MODE} fused={int(fused)} rows={Hs:5d} (N={n}): step {ms*1e3:7.1f} us  match {m*1e3:6.1f} us  compose {c*1e3:6.1f} us  "
           f"-> {H*W/n/ms/1e6:6.2f} G px/s per GPU, strong-scaling efficiency {base/(ms*n):.3f}")
