@@ -85,11 +85,13 @@ struct emo_ctx {
     uint32_t *lut = nullptr;  // 1to1 search index: [256 b][256 g][256 r] keys dist << 22 | tile (index.cu), 64 MiB
     bool lut_valid = false;   // built for the resident library
     uint16_t *lut16 = nullptr;  // compact form: slot of the winner per cell, 32 MiB (index.cu)
-    int lut16_mode = 0;         // 0: none, 1: slot = tile index (T <= 65 536), 2: slot -> idx_entry {tile, colour}
+    int lut16_mode = 0;         // 0: none, 1: slot = tile index (T <= 65 536), 2: slot -> idx_entry {tile, colour}, 3: 2 pending the winner count
     uint32_t lut16_slots = 0;
     uint32_t *idx_slot_of_tile = nullptr;  // build scratch of mode 2
     size_t idx_slot_cap = 0;
     uint2 *idx_entry = nullptr;            // [65 536] {tile, colour} + the winner counter
+    volatile uint32_t *idx_count_host = nullptr;  // pinned: the winner count of the index being built
+    cudaEvent_t idx_count_ev = nullptr;
     int match_mode = 0;       // EMO_MATCH_AUTO / SCAN / INDEX
 
     // scratch

@@ -78,6 +78,8 @@ void emo_destroy(emo_ctx *ctx) {
     cudaFree(ctx->lut16);
     cudaFree(ctx->idx_slot_of_tile);
     cudaFree(ctx->idx_entry);
+    if (ctx->idx_count_host) cudaFreeHost((void *)ctx->idx_count_host);
+    if (ctx->idx_count_ev) cudaEventDestroy(ctx->idx_count_ev);
     cudaFree(ctx->keys);
     cudaFree(ctx->qvec);
     cudaFree(ctx->err_flag);

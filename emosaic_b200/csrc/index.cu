@@ -152,21 +152,32 @@ __host__ __device__ __forceinline__ uint32_t idx16_pos(uint32_t c) {  // c = r |
     return blk << 6 | (c & 3u) | ((c >> 8) & 3u) << 2 | ((c >> 16) & 3u) << 4;
 }
 
-// lut16[idx16_pos(cell)] = slot of the cell's winner; 8 cells (two runs of 4 along r) per thread.  DIRECT: slot = tile index.
+// lut16[idx16_pos(cell)] = slot of the cell's winner.  One thread per 4 x 4 x 4 block of the cube: sixteen 16-byte runs of the
+// 64 MiB table in (neighbouring threads read neighbouring runs), the block's whole 128-byte line out.  DIRECT: slot = tile index.
 template <bool DIRECT>
 __global__ void __launch_bounds__(256) index_compact_kernel(const uint32_t *__restrict__ lut, const uint32_t *__restrict__ slot_of_tile,
                                                             uint16_t *__restrict__ lut16) {
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    const uint4 a = *reinterpret_cast<const uint4 *>(lut + i), b = *reinterpret_cast<const uint4 *>(lut + i + 4);
-    uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;  // rb | gb << 6 | bb << 12
+    const uint32_t rb = blk & 63, gb = (blk >> 6) & 63, bb = blk >> 12;
+    const uint4 *in = reinterpret_cast<const uint4 *>(lut + ((size_t)(bb * 4) << 16 | (size_t)(gb * 4) << 8 | (size_t)(rb * 4)));
+    uint4 *out = reinterpret_cast<uint4 *>(lut16 + ((size_t)blk << 6));
 #pragma unroll
-    for (int m = 0; m < 8; m++) {
-        k[m] &= IDX_TILE_MASK;
-        if (!DIRECT) k[m] = __ldg(slot_of_tile + k[m]);
+    for (int b = 0; b < 4; b++) {
+        uint32_t k[16];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint4 v = __ldg(in + ((size_t)b << 14) + ((size_t)g << 6));  // 65 536 and 256 cells further, in units of 4 cells
+            k[4 * g + 0] = v.x; k[4 * g + 1] = v.y; k[4 * g + 2] = v.z; k[4 * g + 3] = v.w;
+        }
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            k[m] &= IDX_TILE_MASK;
+            if (!DIRECT) k[m] = __ldg(slot_of_tile + k[m]);
+        }
+        // in-block offset = r | g << 2 | b << 4: the 16 cells of one b are 32 consecutive bytes
+        out[2 * b] = make_uint4(k[0] | k[1] << 16, k[2] | k[3] << 16, k[4] | k[5] << 16, k[6] | k[7] << 16);
+        out[2 * b + 1] = make_uint4(k[8] | k[9] << 16, k[10] | k[11] << 16, k[12] | k[13] << 16, k[14] | k[15] << 16);
     }
-    // cells i .. i+3 and i+4 .. i+7 are the r-runs of two neighbouring blocks: 8 bytes each, 8-byte aligned
-    *reinterpret_cast<uint2 *>(lut16 + idx16_pos((uint32_t)i)) = make_uint2(k[0] | k[1] << 16, k[2] | k[3] << 16);
-    *reinterpret_cast<uint2 *>(lut16 + idx16_pos((uint32_t)i + 4)) = make_uint2(k[4] | k[5] << 16, k[6] | k[7] << 16);
 }
 
 // the tables of the index, allocated once per ctx (emo_reserve calls this ahead of the first match)
@@ -188,6 +199,8 @@ int emo_launch_build_index(emo_ctx *ctx) {
     EMO_LAUNCH_CHECK(ctx);
     index_sweep_r_kernel<<<65536 / 8, 256, 0, ctx->stream>>>(ctx->lut);
     EMO_LAUNCH_CHECK(ctx);
+    // (keeping the forward sweep in shared memory instead of in place — one read and one write of the table per axis instead of
+    // two — was measured: 32 KB per warp leaves 6 warps per SM and the axis takes ~55 us instead of 36)
     index_sweep_kernel<1><<<256, 256, 0, ctx->stream>>>(ctx->lut);
     EMO_LAUNCH_CHECK(ctx);
     index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
@@ -199,7 +212,7 @@ int emo_launch_build_index(emo_ctx *ctx) {
     if (wide_only) return EMO_OK;
     if (!ctx->lut16) EMO_CK(cudaMalloc(&ctx->lut16, IDX_CELLS * sizeof(uint16_t)));
     if (ctx->T <= IDX16_SLOTS) {
-        index_compact_kernel<true><<<(uint32_t)(IDX_CELLS / 8 / 256), 256, 0, ctx->stream>>>(ctx->lut, nullptr, ctx->lut16);
+        index_compact_kernel<true><<<(uint32_t)(IDX_CELLS / 64 / 256), 256, 0, ctx->stream>>>(ctx->lut, nullptr, ctx->lut16);
         EMO_LAUNCH_CHECK(ctx);
         ctx->lut16_slots = ctx->T;
         ctx->lut16_mode = 1;  // slot = tile index, colours = the candidate array
@@ -214,14 +227,28 @@ int emo_launch_build_index(emo_ctx *ctx) {
     index_winners_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->lut, ctx->idx_slot_of_tile, ctx->idx_entry,
                                                                         counter);
     EMO_LAUNCH_CHECK(ctx);
-    uint32_t winners = 0;
-    EMO_CK(cudaMemcpyAsync(&winners, counter, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    EMO_CK(cudaStreamSynchronize(ctx->stream));  // once per library: the slot count decides which lookup kernels may run
-    if (winners > IDX16_SLOTS) return EMO_OK;    // too many distinct colours: the 64 MiB table serves every lookup
-    index_compact_kernel<false><<<(uint32_t)(IDX_CELLS / 8 / 256), 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_slot_of_tile, ctx->lut16);
+    // The winner count decides whether the compact table may be used (at most 65 536 slots).  It comes back asynchronously
+    // (pinned word + event) and is looked at when the first lookup is launched; the compaction itself is queued right away —
+    // if there turn out to be too many winners its output is simply never read — so the build has no host round trip inside.
+    if (!ctx->idx_count_host) {
+        EMO_CK(cudaHostAlloc((void **)&ctx->idx_count_host, 16, cudaHostAllocDefault));
+        EMO_CK(cudaEventCreateWithFlags(&ctx->idx_count_ev, cudaEventDisableTiming));
+    }
+    EMO_CK(cudaMemcpyAsync((void *)ctx->idx_count_host, counter, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EMO_CK(cudaEventRecord(ctx->idx_count_ev, ctx->stream));
+    index_compact_kernel<false><<<(uint32_t)(IDX_CELLS / 64 / 256), 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_slot_of_tile, ctx->lut16);
     EMO_LAUNCH_CHECK(ctx);
+    ctx->lut16_mode = 3;  // slot -> {tile, colour} entries, pending the winner count (resolved to 2 or 0 by index16_resolve)
+    return EMO_OK;
+}
+
+// mode 3 -> 2 (compact table usable) or 0 (more than 65 536 distinct colours: the 64 MiB table serves every lookup)
+static int index16_resolve(emo_ctx *ctx) {
+    if (ctx->lut16_mode != 3) return EMO_OK;
+    EMO_CK(cudaEventSynchronize(ctx->idx_count_ev));
+    const uint32_t winners = *ctx->idx_count_host;
     ctx->lut16_slots = winners;
-    ctx->lut16_mode = 2;  // slot -> {tile, colour} entries
+    ctx->lut16_mode = winners <= IDX16_SLOTS ? 2 : 0;
     return EMO_OK;
 }
 
@@ -356,6 +383,7 @@ int emo_launch_match_index(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_
     // The compact table whenever it exists and the buffers allow word accesses (measured on C4: 97 vs 105 us for 16.7 M pixels,
     // 20.8 vs 28.1 us for a 2 M-pixel stripe); EMO_MATCH_INDEX_WIDE forces the 64 MiB table (tests, tuning).
     const bool aligned = (uintptr_t)src % 4 == 0 && (uintptr_t)item % 16 == 0 && (uintptr_t)dist % 16 == 0;
+    if (int rcr = index16_resolve(ctx)) return rcr;
     if (ctx->lut16_mode == 0 || !aligned || Q < 4 || ctx->match_mode == EMO_MATCH_INDEX_WIDE) return launch_index32(ctx, src, Q, item, dist);
     const uint32_t Q4 = Q & ~3u;
     int rc = ctx->lut16_mode == 1 ? launch_index16<1>(ctx, src, Q4, item, dist) : launch_index16<2>(ctx, src, Q4, item, dist);
