@@ -687,11 +687,16 @@ int emo_mosaic(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint32_
 
 }  // extern "C"
 
-// Block rows per pipeline step of emo_mosaic: ~64 MB of output (long enough copies to run at the PCIe rate, short enough that
-// the first and the last chunk — the parts of the pipeline that do not overlap — stay small), but at least ~1.2 M queries per
-// launch when that still leaves >= 8 chunks to overlap (launch-bound lookups / scans on small chunks); at least one block row.
+// Block rows per pipeline step of emo_mosaic.  A chunk is ~1/16 of the output, between 8 and 64 MB: long enough copies to run
+// at the PCIe rate, short enough that the first chunk's kernels and the last chunk's copy — the two ends of the pipeline that
+// overlap with nothing — stay small next to the whole (C2's 201 MB: 16 chunks of 12.6 MB instead of 3 of 67 MB); but at least
+// ~1.2 M queries per launch when that still leaves >= 8 chunks (C4: 293 block rows = 230 MB); at least one block row.
 static uint32_t mosaic_rows_per_chunk(uint32_t bw, uint32_t bh, size_t row_out) {
-    uint32_t rows = (uint32_t)((64ull << 20) / (row_out ? row_out : 1));
+    if (!row_out) row_out = 1;
+    size_t target = row_out * bh / 16;
+    if (target < (8ull << 20)) target = 8ull << 20;
+    if (target > (64ull << 20)) target = 64ull << 20;
+    uint32_t rows = (uint32_t)(target / row_out);
     const uint32_t rows_for_q = ((1200000u + bw - 1) / bw);
     if (rows < rows_for_q && rows_for_q * 8 <= bh) rows = rows_for_q;
     if (rows < 1) rows = 1;
