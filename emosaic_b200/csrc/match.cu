@@ -108,6 +108,8 @@ struct MatchParams {
     const uint32_t *cand;   // [n_chunks*chunk][WORDS]
     uint32_t chunk;         // candidates per stage (multiple of MATCH_WIN)
     uint32_t n_chunks;      // total stages in the candidate array
+    uint32_t last_len;      // candidates scanned in the last stage: what is left of L, rounded up to whole windows
+    uint32_t publish_all;   // 1: whole-range CTAs also leave the search inside the winning window to match_finalize_window_kernel
     uint32_t chunks_per_split;  // stages per split CTA
     uint32_t split_ctas;        // the first split_ctas CTAs of the grid share query tiles: tile = split_tile0 + x / splits, part = x % splits
     uint32_t splits, split_tile0;
@@ -166,9 +168,9 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
     if (warp == CONSUMER_WARPS) {
         // ---- producer warp: one lane streams candidate stages through the ring with TMA bulk copies
         if (lane == 0) {
-            const uint32_t bytes = stage_words * 4;
             for (uint32_t c = c0, n = 0; c < c1; c++, n++) {
                 const int s = n % MATCH_STAGES;
+                const uint32_t bytes = (c + 1 == p.n_chunks ? p.last_len : p.chunk) * (WORDS * 4);
                 if (n >= MATCH_STAGES) mbar_wait_relaxed(&empty[s], ((n / MATCH_STAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&full[s], bytes);
                 bulk_g2s(ring + (size_t)s * stage_words, p.cand + (size_t)c * stage_words, bytes, &full[s]);
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
         mbar_wait(&full[s], (n / MATCH_STAGES) & 1);
         const uint32_t *st = ring + (size_t)s * stage_words;
         const uint32_t cand_base = c * p.chunk;
-        for (uint32_t w0 = 0; w0 < p.chunk; w0 += WIN) {
+        const uint32_t len = c + 1 == p.n_chunks ? p.last_len : p.chunk;  // the padding behind the last window is not scanned
+        for (uint32_t w0 = 0; w0 < len; w0 += WIN) {
             const uint4 *win = reinterpret_cast<const uint4 *>(st + (size_t)w0 * WORDS);
 #pragma unroll(UNR)
             for (int j4 = 0; j4 < WIN / 4; j4++) {
@@ -261,6 +264,16 @@ __global__ void __launch_bounds__(NT + 32, (MINB ? MINB : match_min_blocks<WORDS
         for (int r = 0; r < R; r++) {
             const uint32_t qi = qbase + r * NT + tid;
             if (qi < p.Q) atomicMin(&p.keys[qi], ((unsigned long long)bestd[r] << 32) | idx[r]);
+        }
+        return;
+    }
+    // A launch of few waves ends with every resident CTA in the rescan below at the same time (16 dependent rounds of L2 loads
+    // per query with nothing to overlap them); the finalize kernel does the same search coalesced, one warp per query.
+    if (p.publish_all) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t qi = qbase + r * NT + tid;
+            if (qi < p.Q) p.keys[qi] = ((unsigned long long)bestd[r] << 32) | idx[r];
         }
         return;
     }
@@ -382,9 +395,15 @@ __global__ void __launch_bounds__(256) match_finalize_window_kernel(const MatchP
 template <int WORDS, int R, int NT, int WIN = MATCH_WIN, int MINB = 0, int UNR = MATCH_UNROLL>
 static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     auto kern = match_kernel<WORDS, R, NT, WIN, MINB, UNR>;
-    const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8;
+    static const size_t smem_pad = getenv("EMO_MATCH_SMEM_PAD") ? (size_t)atoi(getenv("EMO_MATCH_SMEM_PAD")) : 0;  // tuning: caps the resident CTAs
+    const size_t smem = (size_t)MATCH_STAGES * p.chunk * WORDS * 4 + 2 * MATCH_STAGES * 8 + smem_pad;
     EMO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t qtiles = (Q + NT * R - 1) / (NT * R);
+    {
+        const uint32_t left = ctx->L - (p.n_chunks - 1) * p.chunk;  // candidates of the last stage, in whole windows
+        p.last_len = (left + WIN - 1) / WIN * WIN;
+        if (p.last_len > p.chunk) p.last_len = p.chunk;
+    }
     // Split the candidate range across gridDim.y when the query tiles cannot fill the resident CTA slots: a split CTA pays a
     // prologue (query gather, pipeline fill) but no epilogue any more (match_finalize_window_kernel), so short ranges are fine:
     // at least 4 stages of candidates per CTA.
@@ -428,19 +447,26 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     p.splits = splits;
     p.split_tile0 = qtiles - split_tiles;
     p.split_ctas = split_tiles * splits;
-    const uint32_t q_begin = p.split_tile0 * (uint32_t)(NT * R);  // queries from here on are merged through the keys
-    if (split_tiles) {
+    const uint32_t q_split = p.split_tile0 * (uint32_t)(NT * R);  // queries from here on are merged through the keys
+    // Few waves: the whole-range CTAs publish (distance, window) as well and the finalize kernel searches every window (C2: 1024
+    // CTAs on 888 slots end in their rescans together).  With many waves a CTA's rescan overlaps its neighbours' scans instead.
+    static const int publish_env = getenv("EMO_MATCH_PUBLISH") ? atoi(getenv("EMO_MATCH_PUBLISH")) : -1;  // tuning / A-B switch
+    p.publish_all = WIN == MATCH_WIN && p.split_tile0 && (publish_env >= 0 ? publish_env != 0 : p.split_tile0 <= 4 * slots);
+    const uint32_t q_begin = p.publish_all ? 0u : q_split;
+    if (split_tiles || p.publish_all) {
         int rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, (size_t)Q * 8);
         if (rc) return rc;
         p.keys = ctx->keys;
-        match_init_keys_kernel<<<(Q - q_begin + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, q_begin);
-        EMO_LAUNCH_CHECK(ctx);
     } else {
         p.keys = nullptr;
     }
+    if (split_tiles) {
+        match_init_keys_kernel<<<(Q - q_split + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys, Q, q_split);
+        EMO_LAUNCH_CHECK(ctx);
+    }
     kern<<<p.split_ctas + p.split_tile0, NT + 32, smem, ctx->stream>>>(p);
     EMO_LAUNCH_CHECK(ctx);
-    if (split_tiles) {
+    if (p.keys) {
         match_finalize_window_kernel<WORDS><<<(Q - q_begin + 7) / 8, 256, 0, ctx->stream>>>(p, q_begin);
         EMO_LAUNCH_CHECK(ctx);
     }
@@ -654,6 +680,8 @@ int emo_launch_match(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, i
     p.chunk = ctx->chunk;
     p.n_chunks = ctx->n_chunks;
     p.chunks_per_split = ctx->n_chunks;
+    p.last_len = ctx->chunk;
+    p.publish_all = 0;
     p.split_ctas = 0; p.splits = 1; p.split_tile0 = 0;
     p.src = src;
     p.W = W;

@@ -39,6 +39,7 @@
 //   resize_horizontal_t_kernel: transposed input, one block per (image, output column), lanes along oy, weights uniform.
 //   resize_copy_kernel: the "(nwidth, nheight) == image.dimensions()" early return of resize() — a plain copy.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -193,6 +194,125 @@ resize_vertical_kernel(const uint8_t *__restrict__ src, size_t img_bytes, uint32
     }
 }
 
+// Two output rows per thread (aligned geometries).  The windows of neighbouring output rows overlap — by 5/6 of their length when
+// the image shrinks — so a thread that owns rows oy and oy + 1 of its NB-byte column loads every source row once and builds
+// 2^23 + b once for both: per byte and tap PRMT / 2 + FFMA + FADD = 2.5 issue slots instead of 3.  The block first lays the two
+// weight rows side by side in shared memory, indexed by source row: {wA, -2^23 wA, wB, -2^23 wB}, zero where a row lies outside a
+// window (a zero tap adds +0 to an accumulator that is never -0: exact), so the loop has no per-row tests; whole groups of four
+// source rows that touch one window only run a single-output body (block-uniform branch).  Source rows are loaded DEPTH groups
+// ahead of their use into register sets that rotate by unrolling.  NB = 8 bytes per thread, or 4 when the grid would not fill
+// the GPU otherwise (a single photo: twice the warps).
+template <bool TRANSPOSED, int DEPTH, int NB>
+__global__ void __launch_bounds__(256)
+resize_vertical2_kernel(const uint8_t *__restrict__ src, size_t img_bytes, uint32_t row_stride, size_t base_off, uint32_t row_bytes,
+                        const uint32_t *__restrict__ left, const uint32_t *__restrict__ cnt, const float *__restrict__ ws,
+                        uint32_t wpitch, float *__restrict__ tmp, uint32_t tpitch, uint32_t nh, uint32_t np, uint32_t n0) {
+    constexpr int NW = NB / 4;  // 32-bit words per row and thread
+    extern __shared__ float4 tab[];  // [4 * ng]
+    const uint32_t oyA = 2 * blockIdx.y, oyB = oyA + 1, n = blockIdx.z + n0;
+    const bool hasB = oyB < nh;
+    const uint32_t lA = left[oyA], eA = lA + cnt[oyA];
+    const uint32_t lB = hasB ? left[oyB] : eA, eB = hasB ? lB + cnt[oyB] : eA;  // lA <= lB and eA <= eB (checked on the host)
+    const uint32_t span = eB - lA, ng = (span + 3) / 4;
+    for (uint32_t j = threadIdx.x; j < 4 * ng; j += blockDim.x) {
+        const uint32_t r = lA + j;
+        const float wA = r < eA ? __ldg(ws + (size_t)oyA * wpitch + j) : 0.0f;
+        const float wB = (r >= lB && r < eB) ? __ldg(ws + (size_t)oyB * wpitch + (r - lB)) : 0.0f;
+        tab[j] = make_float4(wA, wA * -8388608.0f, wB, wB * -8388608.0f);  // a power of two: exact
+    }
+    __syncthreads();
+    const uint32_t xb = (blockIdx.x * blockDim.x + threadIdx.x) * NB;
+    if (xb >= row_bytes) return;
+    // the aligned 8-byte word that holds a byte of the view lies inside the image row (row starts and strides are multiples of 8)
+    const uint8_t *pl = src + (size_t)n * img_bytes + base_off + (size_t)lA * row_stride + xb;  // first row of the next group to load
+    uint32_t gl = 0;
+    const uint32_t last = span - 1;
+    const uint32_t gA_end = (eA - lA + 3) / 4;         // groups below touch window A
+    const uint32_t gB_beg = hasB ? (lB - lA) / 4 : ng;  // groups from here on touch window B
+    float tA[NB], tB[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) tA[k] = tB[k] = 0.0f;
+    auto load_row = [&](uint32_t (&w)[NW], const uint8_t *q) {
+        if (NW == 2) {
+            const uint2 t = __ldg((const uint2 *)q);
+            w[0] = t.x; w[NW - 1] = t.y;
+        } else {
+            w[0] = __ldg((const uint32_t *)q);
+        }
+    };
+    // the next group's rows into v; only the last group can reach beyond the span (its extra rows have zero weights: any row will do)
+    auto load_next = [&](uint32_t (&v)[4][NW]) {
+        if (gl + 1 < ng) {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) load_row(v[k], pl + (size_t)k * row_stride);
+            pl += 4 * (size_t)row_stride;
+        } else if (gl < ng) {
+            const uint32_t left_rows = last - 4 * gl;  // >= 0: the group holds at least one row of the span
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) load_row(v[k], pl + (size_t)min(k, left_rows) * row_stride);
+        }
+        gl++;
+    };
+    auto taps = [&](const uint32_t (&v)[4][NW], uint32_t g) {
+        const float4 *tg = tab + 4 * g;
+        const bool a = g < gA_end, b = g >= gB_beg;
+        if (a && b) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 w = tg[k];
+#pragma unroll
+                for (int h = 0; h < NW; h++) {
+                    tap4(tA + 4 * h, v[k][h], w.x, w.y);
+                    tap4(tB + 4 * h, v[k][h], w.z, w.w);
+                }
+            }
+        } else if (a) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 w = *(const float2 *)(tg + k);
+#pragma unroll
+                for (int h = 0; h < NW; h++) tap4(tA + 4 * h, v[k][h], w.x, w.y);
+            }
+        } else if (b) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 w = *((const float2 *)(tg + k) + 1);
+#pragma unroll
+                for (int h = 0; h < NW; h++) tap4(tB + 4 * h, v[k][h], w.x, w.y);
+            }
+        }
+    };
+    uint32_t v[DEPTH + 1][4][NW];
+#pragma unroll
+    for (int s = 0; s < DEPTH; s++) load_next(v[s]);
+    for (uint32_t g = 0; g < ng; g += DEPTH + 1) {
+#pragma unroll
+        for (int s = 0; s <= DEPTH; s++) {
+            load_next(v[(s + DEPTH) % (DEPTH + 1)]);
+            if (g + s < ng) taps(v[s], g + s);
+        }
+    }
+    if (TRANSPOSED) {
+        // [x*3+c][oy], np floats per line; the padding lines of the last group exist in the buffer
+        float *o = tmp + ((size_t)blockIdx.z * tpitch + xb) * np + oyA;
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            if (hasB) *(float2 *)(o + k * (size_t)np) = make_float2(tA[k], tB[k]);  // oyA is even, np a multiple of 32
+            else o[k * (size_t)np] = tA[k];
+        }
+    } else {
+        // rows are padded to a multiple of 8 floats: the padding lanes of the last group are never read
+        float4 *o = (float4 *)(tmp + ((size_t)blockIdx.z * nh + oyA) * tpitch + xb);
+#pragma unroll
+        for (int h = 0; h < NW; h++) o[h] = make_float4(tA[4 * h], tA[4 * h + 1], tA[4 * h + 2], tA[4 * h + 3]);
+        if (hasB) {
+            o = (float4 *)((float *)o + tpitch);
+#pragma unroll
+            for (int h = 0; h < NW; h++) o[h] = make_float4(tB[4 * h], tB[4 * h + 1], tB[4 * h + 2], tB[4 * h + 3]);
+        }
+    }
+}
+
 __device__ __forceinline__ uint8_t clamp_round_u8(float t) {
     // sample.rs: NumCast::from(FloatNearest(clamp(t, 0.0, 255.0))): clamp, then f32::round (half away from zero)
     t = t < 0.0f ? 0.0f : (t > 255.0f ? 255.0f : t);
@@ -303,6 +423,7 @@ struct emo_resize_state {
     uint32_t *d_tab = nullptr;  // device: left_v | cnt_v | left_h | cnt_h | ws_v [nh][pv] | -2^23 ws_v | ws_h tap-major [ph][nw] | ws_h [nw][ph]
     size_t d_tab_cap = 0;
     bool uploaded = false;
+    uint32_t pair_span = 0;  // longest run of source rows two neighbouring output rows cover together; 0: windows not monotone
     float *tmp = nullptr;
     size_t tmp_cap = 0;
 };
@@ -330,7 +451,17 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     }
     if (!ctx->resize) ctx->resize = new emo_resize_state();
     emo_resize_state &st = *ctx->resize;
-    if (st.v.n_in != ch || st.v.n_out != nh) { resize_axis(ch, nh, st.v); st.uploaded = false; }
+    if (st.v.n_in != ch || st.v.n_out != nh) {
+        resize_axis(ch, nh, st.v);
+        st.uploaded = false;
+        st.pair_span = 1;
+        for (uint32_t o = 0; o < nh && st.pair_span; o += 2) {
+            const uint32_t lA = st.v.left[o], eA = lA + st.v.cnt[o];
+            const uint32_t lB = o + 1 < nh ? st.v.left[o + 1] : eA, eB = o + 1 < nh ? lB + st.v.cnt[o + 1] : eA;
+            if (lA > lB || eA > eB) st.pair_span = 0;
+            else if (eB - lA > st.pair_span) st.pair_span = eB - lA;
+        }
+    }
     if (st.h.n_in != cw || st.h.n_out != nw) { resize_axis(cw, nw, st.h); st.uploaded = false; }
     const uint32_t pv = (st.v.pitch + 3) / 4 * 4, ph = st.h.pitch;  // vertical weight rows padded for 128-bit loads
     // every section starts on a 16-byte boundary
@@ -391,6 +522,30 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     for (uint32_t z0 = 0; z0 < n; z0 += per_pass) {
         const uint32_t nz = n - z0 < per_pass ? n - z0 : per_pass;
         const dim3 gv((groups + 255) / 256, nh, nz);
+        const size_t pair_smem = (size_t)(st.pair_span + 3) / 4 * 4 * sizeof(float4);
+        static const bool pair_off = getenv("EMO_RESIZE_PAIR") && atoi(getenv("EMO_RESIZE_PAIR")) == 0;  // A-B switch
+        if (aligned && st.pair_span && pair_smem <= 48 * 1024 && !pair_off) {
+            // 8 bytes per thread and loads one group ahead keep a full grid busy; a grid of at most one wave (a single photo: 192
+            // blocks) takes 4 bytes per thread — twice the warps — and three groups in flight
+            static const int depth_env = getenv("EMO_RESIZE_DEPTH") ? atoi(getenv("EMO_RESIZE_DEPTH")) : 0;  // tuning overrides
+            static const int nb_env = getenv("EMO_RESIZE_NB") ? atoi(getenv("EMO_RESIZE_NB")) : 0;
+            const bool small = (uint64_t)((groups + 255) / 256) * ((nh + 1) / 2) * nz <= 4ull * ctx->sm_count;
+            const int depth = depth_env ? depth_env : (small ? 3 : 1), nb = nb_env ? nb_env : (small ? 4 : 8);
+            const uint32_t cols = tpitch / nb;  // threads per row
+            const uint32_t bs = small ? 128 : (cols >= 256 ? 256 : (cols + 31) / 32 * 32);
+            const dim3 g2((cols + bs - 1) / bs, (nh + 1) / 2, nz);
+#define EMO_VERTICAL2(T, P, B)                                                                                                     \
+    resize_vertical2_kernel<T, P, B><<<g2, bs, pair_smem, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv, \
+                                                                         d_wv, pv, st.tmp, tpitch, nh, np, z0)
+            if (transposed) {
+                if (nb == 4) { if (depth == 1) EMO_VERTICAL2(true, 1, 4); else EMO_VERTICAL2(true, 3, 4); }
+                else if (depth == 1) EMO_VERTICAL2(true, 1, 8); else EMO_VERTICAL2(true, 3, 8);
+            } else {
+                if (nb == 4) { if (depth == 1) EMO_VERTICAL2(false, 1, 4); else EMO_VERTICAL2(false, 3, 4); }
+                else if (depth == 1) EMO_VERTICAL2(false, 1, 8); else EMO_VERTICAL2(false, 3, 8);
+            }
+#undef EMO_VERTICAL2
+        } else
 #define EMO_VERTICAL(A, T)                                                                                                         \
     resize_vertical_kernel<A, T><<<gv, 256, 0, ctx->stream>>>(images, img_bytes, row_stride, base_off, row_bytes, d_lv, d_cv, d_wv, d_nv, pv, \
                                                              st.tmp, tpitch, nh, np, z0)
