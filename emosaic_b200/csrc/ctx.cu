@@ -677,6 +677,8 @@ int emo_mosaic_dev(emo_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uin
     EMO_REQUIRE(oc == 3 || (uintptr_t)out % 4 == 0, EMO_ERR_ARG, "mosaic: RGBA output must be 4-byte aligned");
     EMO_CK(cudaSetDevice(ctx->device));
     if ((rc = emo_prepare_match(ctx, (uint64_t)(W / ctx->dim) * (H / ctx->dim)))) return rc;
+    // (Replaying a captured graph of the two launches was measured and dropped: 592.3 vs 590.0 us per C4 step and 80.7 vs 78.7 us on
+    // a 512-row stripe — the programmatic-dependent launches on the stream already overlap the launch gaps)
     return mosaic_launch(ctx, src, W, H, oc, tint_alpha, item, dist, out);
 }
 

@@ -346,10 +346,13 @@ resize_horizontal_kernel(const float *__restrict__ tmp, uint32_t tpitch, const u
 // Row-major intermediate, windows of neighbouring outputs far apart: stage the row in shared memory first.
 __device__ __forceinline__ uint32_t skew(uint32_t e) { return e + (e >> 5); }
 
-__global__ void __launch_bounds__(256)
+// WS: the tap-major weights are staged too — with few blocks (the 64 rows of a single photo -> tile) every thread is a chain of
+// dependent loads per tap, and a shared-memory load is ten times shorter than one from L2.
+template <bool WS>
+__global__ void __launch_bounds__(512)
 resize_horizontal_smem_kernel(const float *__restrict__ tmp, uint32_t tpitch, uint32_t row_floats, const uint32_t *__restrict__ left,
                               const uint32_t *__restrict__ cnt, const float *__restrict__ wsT, uint32_t nw, uint32_t nh,
-                              uint8_t *__restrict__ out, uint32_t n0) {
+                              uint32_t w_words, uint32_t w_off, uint8_t *__restrict__ out, uint32_t n0) {
     extern __shared__ float srow[];
     const uint32_t y = blockIdx.x, n = blockIdx.y + n0;
     const float *__restrict__ row = tmp + ((size_t)blockIdx.y * nh + y) * tpitch;
@@ -361,15 +364,18 @@ resize_horizontal_smem_kernel(const float *__restrict__ tmp, uint32_t tpitch, ui
         srow[s + 2] = v.z;
         srow[s + 3] = v.w;
     }
+    float *sw = srow + w_off;  // [taps][nw]
+    if (WS)
+        for (uint32_t e = threadIdx.x; e < w_words; e += blockDim.x) sw[e] = __ldg(wsT + e);
     __syncthreads();
     for (uint32_t ox = threadIdx.x; ox < nw; ox += blockDim.x) {
         const uint32_t c = cnt[ox];
         const uint32_t base = left[ox] * 3;
-        const float *__restrict__ w = wsT + ox;
+        const float *__restrict__ w = (WS ? sw : wsT) + ox;
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
 #pragma unroll 4
         for (uint32_t i = 0; i < c; i++) {
-            const float wi = __ldg(w + (size_t)i * nw);
+            const float wi = WS ? w[(size_t)i * nw] : __ldg(w + (size_t)i * nw);
             const uint32_t e = base + 3 * i;
             t0 = __fadd_rn(t0, __fmul_rn(srow[skew(e)], wi));
             t1 = __fadd_rn(t1, __fmul_rn(srow[skew(e + 1)], wi));
@@ -395,7 +401,7 @@ resize_horizontal_t_kernel(const float *__restrict__ tmpT, uint32_t tpitch, uint
     const float *__restrict__ col = tmpT + ((size_t)blockIdx.z * tpitch + (size_t)left[ox] * 3) * np + oy;
     const float *__restrict__ w = ws + (size_t)ox * wpitch;
     float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t i = 0; i < c; i++, col += 3 * (size_t)np) {
         const float wi = __ldg(w + i);
         t0 = __fadd_rn(t0, __fmul_rn(__ldg(col), wi));
@@ -517,8 +523,13 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
     // row-major intermediate with outputs 4+ source pixels apart: stage each row in shared memory (skewed), if it fits
     const size_t smem_row = ((size_t)tpitch + tpitch / 32 + 8) * 4;
     const bool staged = !transposed && cw >= 4 * (uint64_t)nw && smem_row <= 200 * 1024;
-    if (staged && smem_row > 48 * 1024)
-        EMO_CK(cudaFuncSetAttribute(resize_horizontal_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // few blocks (at most one per SM): the weights go to shared memory as well, if they fit
+    const size_t w_words = (size_t)ph * nw, w_off = (smem_row / 4 + 3) / 4 * 4;
+    const bool staged_w = staged && (uint64_t)nh * n <= (uint64_t)ctx->sm_count && (w_off + w_words) * 4 <= 200 * 1024;
+    const size_t smem_h = staged_w ? (w_off + w_words) * 4 : smem_row;
+    if (staged && smem_h > 48 * 1024)
+        EMO_CK(cudaFuncSetAttribute(staged_w ? resize_horizontal_smem_kernel<true> : resize_horizontal_smem_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     for (uint32_t z0 = 0; z0 < n; z0 += per_pass) {
         const uint32_t nz = n - z0 < per_pass ? n - z0 : per_pass;
         const dim3 gv((groups + 255) / 256, nh, nz);
@@ -561,9 +572,16 @@ int emo_launch_resize(emo_ctx *ctx, const uint8_t *images, uint32_t n, uint32_t 
             resize_horizontal_t_kernel<<<dim3(nw, (nh + bt - 1) / bt, nz), bt, 0, ctx->stream>>>(st.tmp, tpitch, np, d_lh, d_ch, d_whr, ph,
                                                                                                nw, nh, out, z0);
         } else if (staged) {
-            const uint32_t bt = nw >= 256 ? 256 : (nw + 31) / 32 * 32;
-            resize_horizontal_smem_kernel<<<dim3(nh, nz), bt, smem_row, ctx->stream>>>(st.tmp, tpitch, row_bytes, d_lh, d_ch, d_wh, nw,
-                                                                                      nh, out, z0);
+            // the staging loop wants many loads in flight whatever the number of outputs: a thread per 32 floats of the row
+            uint32_t bt = (row_bytes / 32 + 31) / 32 * 32;
+            if (bt < (nw + 31) / 32 * 32) bt = (nw + 31) / 32 * 32;
+            bt = bt > 512 ? 512 : (bt < 32 ? 32 : bt);
+            if (staged_w)
+                resize_horizontal_smem_kernel<true><<<dim3(nh, nz), bt, smem_h, ctx->stream>>>(st.tmp, tpitch, row_bytes, d_lh, d_ch, d_wh, nw, nh,
+                                                                                              (uint32_t)w_words, (uint32_t)w_off, out, z0);
+            else
+                resize_horizontal_smem_kernel<false><<<dim3(nh, nz), bt, smem_h, ctx->stream>>>(st.tmp, tpitch, row_bytes, d_lh, d_ch, d_wh, nw,
+                                                                                               nh, 0u, 0u, out, z0);
         } else {
             resize_horizontal_kernel<<<dim3((nw + 127) / 128, nh, nz), 128, 0, ctx->stream>>>(st.tmp, tpitch, d_lh, d_ch, d_wh, nw, nh,
                                                                                             out, z0);

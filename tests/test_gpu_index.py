@@ -216,6 +216,69 @@ def test_mosaic_dev(ictx, ts, bh, bw):
     assert (out.cpu().numpy()[:OB].reshape(bh * ts, bw * ts, 3) == oracle.render(tiles_h, ri)).all()
 
 
+def test_mosaic_dev_repeated_calls_and_state_changes(ictx):
+    """emo_mosaic_dev called over and over on the same buffers (the steady state of a frame loop, and of bench.py): every call
+    must see the new buffer contents, and library, match mode, tint and geometry may change between calls.  Every call is checked
+    against the oracle."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(909)
+    T, ts, bh, bw = 700, 8, 24, 96
+    Q, OB = bh * bw, bh * ts * bw * ts * 3
+
+    def library():
+        tiles = rng.integers(0, 256, (T, ts, ts, 3), dtype=np.uint8)
+        colors = ictx.analyse_tiles(tiles, 1)
+        ictx.set_library(colors, tiles)
+        return tiles, colors
+
+    tiles_h, colors = library()
+    ictx.set_match_mode("index")
+    ictx.build_index()
+    src = torch.zeros(Q * 3, dtype=torch.uint8, device=dev)
+    item = torch.zeros(Q, dtype=torch.int32, device=dev)
+    dist = torch.zeros(Q, dtype=torch.int32, device=dev)
+    out = torch.zeros(OB, dtype=torch.uint8, device=dev)
+    out4 = torch.zeros(bh * ts * bw * ts * 4, dtype=torch.uint8, device=dev)
+
+    def step(oc=3, alpha=0, rows=bh):
+        src_h = rng.integers(0, 256, (bh, bw, 3), dtype=np.uint8)
+        src.copy_(torch.from_numpy(src_h.reshape(-1)).to(dev))
+        item.fill_(0); dist.fill_(0); out.fill_(0); out4.fill_(0)
+        torch.cuda.synchronize()
+        n0 = ictx.launch_count()
+        ictx.mosaic_dev(src.data_ptr(), bw, rows, oc, alpha, item.data_ptr(), dist.data_ptr(), (out if oc == 3 else out4).data_ptr())
+        ictx.sync()
+        ri, rd = oracle.match(colors, src_h[:rows])
+        q = rows * bw
+        assert (item.cpu().numpy()[:q] == ri.reshape(-1)).all() and (dist.cpu().numpy()[:q] == rd.reshape(-1)).all()
+        want = oracle.render(tiles_h, ri)
+        if oc == 3:
+            assert (out.cpu().numpy()[:q * ts * ts * 3].reshape(rows * ts, bw * ts, 3) == want).all()
+        else:
+            assert (out4.cpu().numpy()[:q * ts * ts * 4].reshape(rows * ts, bw * ts, 4) == oracle.tint(want, src_h[:rows], alpha)).all()
+        return ictx.launch_count() - n0
+
+    assert [step() for _ in range(5)] == [2] * 5          # new pixels every time
+    tiles_h, colors = library()                           # same shape, new tiles: the index is rebuilt
+    for _ in range(4):
+        step()
+    for _ in range(3):
+        step(rows=bh - 5)                                  # another geometry ...
+    for _ in range(3):
+        step()                                             # ... and back
+    for _ in range(3):
+        step(oc=4, alpha=127)                              # tint tables are built on the first of these
+    for _ in range(3):
+        step(oc=4, alpha=60)
+    ictx.set_match_mode("scan")
+    for _ in range(4):
+        step()
+    ictx.set_match_mode("index")
+    for _ in range(3):
+        step()
+
+
 def test_mosaic_dev_4to1_and_errors(ictx):
     torch = pytest.importorskip("torch")
     dev = torch.device("cuda", 0)

@@ -85,6 +85,25 @@ def test_resize_tile_batches_transposed_path(ctx, n, h, w, view, ts):
     assert (got == want).all()
 
 
+def test_resize_full_grids_paired_rows_kernel(ctx):
+    """Aligned geometries whose grids exceed one wave take the paired-rows vertical kernel in its 8-bytes-per-thread, one-group-
+    ahead shape (resize.cu; smaller grids take 4 bytes and three groups): a batch through the transposed intermediate, a row-major
+    down-scale with an odd number of output rows (the last pair has one row), an up-scale (windows of neighbouring rows coincide
+    or leave gaps) and a view at an 8-byte aligned offset."""
+    rng = np.random.default_rng(77)
+    batch = rng.integers(0, 256, (80, 512, 512, 3), dtype=np.uint8)
+    got = ctx.resize(batch, 64, 64)
+    for k in (0, 41, 79):
+        assert (got[k] == oracle.resize_lanczos3(batch[k], 64, 64)).all()
+    big = rng.integers(0, 256, (2048, 2048, 3), dtype=np.uint8)
+    big[300:900, 200:1500] = _photo(rng, 600, 1300)
+    assert (ctx.resize(big, 1024, 1023) == oracle.resize_lanczos3(big, 1024, 1023)).all()
+    view = (8, 3, 2024, 2040)
+    assert (ctx.resize(big, 700, 701, view) == oracle.resize_lanczos3(big, 700, 701, view)).all()
+    small = rng.integers(0, 256, (640, 640, 3), dtype=np.uint8)
+    assert (ctx.resize(small, 640, 2049) == oracle.resize_lanczos3(small, 640, 2049)).all()
+
+
 def test_resize_device_pointers_unaligned_and_guarded(ctx):
     """Device-pointer entry: odd base addresses (byte path), canaries around the output."""
     torch = pytest.importorskip("torch")

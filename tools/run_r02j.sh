@@ -1,10 +1,5 @@
-timeout 120 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread --clock-control none -k regex:resize_ -c 60 --csv --log-file gpurun_out/r02j_resize_launches.csv python tools/bench_resize.py 3 4 6 > /dev/null 2>&1; echo "list rc=$?"
-python - <<PY
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/r02j_resize_launches.csv')) if len(r)>10]
-h=rows[0]; ki=h.index('Kernel Name'); mi=h.index('Metric Name'); vi=h.index('Metric Value'); ii=h.index('ID'); gi=h.index('Grid Size'); bi=h.index('Block Size')
-d={}
-for r in rows[1:]: d.setdefault((int(r[ii]),r[ki][:44],r[gi],r[bi]),{})[r[mi][:24]]=r[vi]
-for k in sorted(d):
-    if k[0] % 16 in (4,5): print(k, d[k])
-PY
+timeout 600 python -m pytest tests/test_gpu_resize.py -x -q 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_index.py -x -q -k "mosaic_dev" 2>&1 | tail -2
+for G in 0 1; do echo "EMO_GRAPH=$G"; EMO_GRAPH=$G FUSED=1 timeout 300 python tools/bench_stripes.py; done
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:resize_ -c 40 --csv --log-file gpurun_out/r02j_resize_launches.csv python tools/bench_resize.py 4 > /dev/null 2>&1; echo "list rc=$?"
+python tools/summarise_ncu.py launches gpurun_out/r02j_resize_launches.csv
