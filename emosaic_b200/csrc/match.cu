@@ -346,14 +346,19 @@ __global__ void match_finalize_kernel(const unsigned long long *__restrict__ key
     dist[i] = (uint32_t)(k >> 32);
 }
 
-// Split mode, second half: keys[q] = distance << 32 | first candidate of the window that holds the winner.  One warp per
-// query: lane l takes candidates 4l .. 4l + 3 of the window (WIN = 128 = 32 lanes x 4), the first lane / candidate whose distance
-// equals the minimum is the canonical winner (smallest rank).  Coalesced, no dependent chain: microseconds for a whole stripe.
+// Split mode, second half: keys[q] = distance << 32 | first candidate of the window that holds the winner.  Eight lanes per
+// query: lane l of the group takes candidates 16l .. 16l + 15 of the window (WIN = 128) in four batches of 128-bit loads, the
+// first candidate whose distance equals the minimum is the canonical winner (smallest rank).  Coalesced, no dependent chain.
+// (One warp per query spent most of its instructions assembling the same query vector in all 32 lanes: 112 us for C2's
+// 227 000 queries, half of them ALU-pipe cycles.)
 template <int WORDS>
 __global__ void __launch_bounds__(256) match_finalize_window_kernel(const MatchParams p, uint32_t q_begin) {
-    static_assert(MATCH_WIN == 128, "one lane per 4 candidates");
-    const uint32_t qi = q_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (qi >= p.Q) return;
+    static_assert(MATCH_WIN == 128, "eight lanes x 16 candidates");
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sub = threadIdx.x & 7, grp = (threadIdx.x & 31) >> 3;
+    uint32_t qi = q_begin + (t >> 3);
+    const bool live = qi < p.Q;
+    if (!live) qi = p.Q - 1;  // keeps the warp whole for the ballot
     const unsigned long long k = p.keys[qi];
     const uint32_t best = (uint32_t)(k >> 32), w0 = (uint32_t)k;
     uint32_t q[WORDS];
@@ -369,23 +374,26 @@ __global__ void __launch_bounds__(256) match_finalize_window_kernel(const MatchP
             q[b >> 2] |= v << (8 * (b & 3));
         }
     }
-    const uint4 *wc = reinterpret_cast<const uint4 *>(p.cand + ((size_t)w0 + 4 * lane) * WORDS);
-    uint32_t cw[4 * WORDS];
+    const uint4 *wc = reinterpret_cast<const uint4 *>(p.cand + ((size_t)w0 + 16 * sub) * WORDS);
+    uint32_t found = 16;
 #pragma unroll
-    for (int v = 0; v < WORDS; v++) {
-        const uint4 t4 = __ldg(wc + v);
-        cw[4 * v + 0] = t4.x; cw[4 * v + 1] = t4.y; cw[4 * v + 2] = t4.z; cw[4 * v + 3] = t4.w;
+    for (int g = 3; g >= 0; g--) {
+        uint32_t cw[4 * WORDS];
+#pragma unroll
+        for (int v = 0; v < WORDS; v++) {
+            const uint4 t4 = __ldg(wc + g * WORDS + v);
+            cw[4 * v + 0] = t4.x; cw[4 * v + 1] = t4.y; cw[4 * v + 2] = t4.z; cw[4 * v + 3] = t4.w;
+        }
+        if (sad_vec<WORDS, 3 * WORDS>(q, cw, 0u) == best) found = 4 * g + 3;
+        if (sad_vec<WORDS, 2 * WORDS>(q, cw, 0u) == best) found = 4 * g + 2;
+        if (sad_vec<WORDS, 1 * WORDS>(q, cw, 0u) == best) found = 4 * g + 1;
+        if (sad_vec<WORDS, 0 * WORDS>(q, cw, 0u) == best) found = 4 * g + 0;
     }
-    uint32_t found = 4;
-    if (sad_vec<WORDS, 3 * WORDS>(q, cw, 0u) == best) found = 3;
-    if (sad_vec<WORDS, 2 * WORDS>(q, cw, 0u) == best) found = 2;
-    if (sad_vec<WORDS, 1 * WORDS>(q, cw, 0u) == best) found = 1;
-    if (sad_vec<WORDS, 0 * WORDS>(q, cw, 0u) == best) found = 0;
-    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, found < 4);
+    const uint32_t hit = (__ballot_sync(0xFFFFFFFFu, found < 16) >> (8 * grp)) & 0xFFu;
     const uint32_t first = hit ? (uint32_t)__ffs((int)hit) - 1 : 0;  // hit != 0: the window was chosen because it reaches `best`
-    const uint32_t pos = __shfl_sync(0xFFFFFFFFu, found, first);
-    if (lane == 0) {
-        const uint32_t cnd = w0 + 4 * first + (pos < 4 ? pos : 0);
+    const uint32_t pos = __shfl_sync(0xFFFFFFFFu, found, 8 * grp + first);
+    if (sub == 0 && live) {
+        const uint32_t cnd = w0 + 16 * first + (pos < 16 ? pos : 0);
         const int32_t t1 = (int32_t)(p.mirrored ? (cnd >> 1) : cnd) + 1;
         p.item[qi] = (p.mirrored && (cnd & 1)) ? -t1 : t1;
         p.dist[qi] = best;
@@ -412,8 +420,8 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     if (occ < 1) occ = 1;
     const uint32_t slots = (uint32_t)ctx->sm_count * (uint32_t)occ;
     // Which query tiles share their candidate range between several CTAs:
-    //  - fewer tiles than resident slots: all of them, enough parts for 1.5 x the slots (C2's row stripes, tools/sweep_match3.py,
-    //    MINLENS=0: 64 block rows 204 -> 172 us, 32 rows 204 -> 104 us; splitting a grid that already fills the slots costs 8 %);
+    //  - fewer tiles than resident slots: all of them, the number of parts from the cost model below (C2's row stripes,
+    //    tools/sweep_match3.py: 64 block rows 204 us unsplit, 162 us in 8 parts; splitting a grid that already fills the slots costs 8 %);
     //  - a small ragged last wave (rem = tiles % slots <= slots / 8): only those rem tiles, slots / rem parts each, so that the
     //    remainder fills the machine next to the whole-range CTAs instead of running one CTA per SM after them.  Without it the
     //    time is a staircase — 888 tiles 954 us, anything from 889 to 1024 tiles 1105 us on C2's library — with it 896 tiles take
@@ -421,13 +429,22 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     // A part is at least 4 stages long.
     uint32_t splits = 1, split_tiles = 0;
     const uint32_t max_parts = p.n_chunks / 4;
-    static const uint32_t fill_num = getenv("EMO_MATCH_FILL") ? (uint32_t)atoi(getenv("EMO_MATCH_FILL")) : 150u;  // tuning: % of the slots
     static const bool tail_on = !(getenv("EMO_MATCH_TAIL") && atoi(getenv("EMO_MATCH_TAIL")) == 0);            // tuning / A-B switch
     if (qtiles < slots) {
-        const uint32_t by_fill = (fill_num * slots / 100u + qtiles - 1) / qtiles;
+        // Parts per tile from a cost model fitted to tools/sweep_match3.py on C2's stripes (EMO_MATCH_SPLITS = 2 ... 10 on 32 - 256 block
+        // rows): an SM works through its ceil(CTAs / SMs) CTAs at a constant rate once it holds three or more, a CTA costs its
+        // stages plus ~0.3 of a stage for the prologue and the publish, so time ~ ceil(tiles * S / SMs) * (ceil(stages / S) + 0.3).
+        // Even parts matter more than their number: 40 stages in 8 parts beat 6 parts (7,7,7,7,7,5) by 14 % on 64 rows.
+        uint64_t best_cost = ~0ull;
+        const uint32_t hi = max_parts ? max_parts : 1;
+        for (uint32_t s = 1; s <= hi; s++) {
+            const uint64_t ctas = (uint64_t)qtiles * s, per_sm = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+            uint64_t cost = per_sm * (10ull * ((p.n_chunks + s - 1) / s) + 3);
+            if (ctas < 3ull * ctx->sm_count) cost = cost * 108 / 100;  // too few warps per SM to keep the ALU pipe busy
+            if (cost < best_cost) { best_cost = cost; splits = s; }
+        }
         static const uint32_t min_len = getenv("EMO_MATCH_MINLEN") ? (uint32_t)atoi(getenv("EMO_MATCH_MINLEN")) : 0u;  // tuning override
-        const uint32_t by_len = min_len ? (p.n_chunks * p.chunk) / min_len : max_parts;
-        splits = by_fill < by_len ? by_fill : by_len;
+        if (min_len && splits > (p.n_chunks * p.chunk) / min_len) splits = (p.n_chunks * p.chunk) / min_len;
         split_tiles = qtiles;
     } else if (tail_on) {
         const uint32_t rem = qtiles % slots;
@@ -448,10 +465,11 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     p.split_tile0 = qtiles - split_tiles;
     p.split_ctas = split_tiles * splits;
     const uint32_t q_split = p.split_tile0 * (uint32_t)(NT * R);  // queries from here on are merged through the keys
-    // Few waves: the whole-range CTAs publish (distance, window) as well and the finalize kernel searches every window (C2: 1024
-    // CTAs on 888 slots end in their rescans together).  With many waves a CTA's rescan overlaps its neighbours' scans instead.
-    static const int publish_env = getenv("EMO_MATCH_PUBLISH") ? atoi(getenv("EMO_MATCH_PUBLISH")) : -1;  // tuning / A-B switch
-    p.publish_all = WIN == MATCH_WIN && p.split_tile0 && (publish_env >= 0 ? publish_env != 0 : p.split_tile0 <= 4 * slots);
+    // EMO_MATCH_PUBLISH=1 (A-B switch, off by default): the whole-range CTAs publish (distance, window) as well and the finalize
+    // kernel searches every window.  Measured on C2 (1024 CTAs on 888 slots, which end in their rescans together): the scan
+    // itself 946 -> 922 us, but the finalize kernel costs more than the 24 us it saves.
+    static const bool publish_env = getenv("EMO_MATCH_PUBLISH") && atoi(getenv("EMO_MATCH_PUBLISH")) > 0;
+    p.publish_all = WIN == MATCH_WIN && p.split_tile0 && publish_env;
     const uint32_t q_begin = p.publish_all ? 0u : q_split;
     if (split_tiles || p.publish_all) {
         int rc = emo_ensure(ctx, (void **)&ctx->keys, &ctx->keys_cap, (size_t)Q * 8);
@@ -467,7 +485,7 @@ static int launch_match_t(emo_ctx *ctx, MatchParams &p, uint32_t Q) {
     kern<<<p.split_ctas + p.split_tile0, NT + 32, smem, ctx->stream>>>(p);
     EMO_LAUNCH_CHECK(ctx);
     if (p.keys) {
-        match_finalize_window_kernel<WORDS><<<(Q - q_begin + 7) / 8, 256, 0, ctx->stream>>>(p, q_begin);
+        match_finalize_window_kernel<WORDS><<<(Q - q_begin + 31) / 32, 256, 0, ctx->stream>>>(p, q_begin);
         EMO_LAUNCH_CHECK(ctx);
     }
     return EMO_OK;
