@@ -124,6 +124,45 @@ __global__ void __launch_bounds__(256) index_sweep_kernel(uint32_t *__restrict__
     }
 }
 
+// The same pass with the line in registers: one read and one write of the table per axis instead of two of each.  A CTA of
+// 8 warps takes a slab of 256 positions along the axis x 32 neighbouring r (every access of a warp is one 128-byte row); warp w
+// owns positions 32w .. 32w + 31 of all 32 lines, a thread its 32 keys of one line.  Inside a thread the forward and backward
+// sweeps run over registers; between warps only the two boundary keys travel (shared memory, 2 x 8 x 32 words): the forward
+// carry into a segment is the minimum over the earlier segments of their local end value + the distance, which is exactly what
+// a sweep over the whole line would have brought along.
+template <int AXIS>  // 1: g, 2: b
+__global__ void __launch_bounds__(256) index_sweep_reg_kernel(uint32_t *__restrict__ lut) {
+    __shared__ uint32_t carry[2][8][32];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t r = (blockIdx.x & 7) * 32 + lane, o = blockIdx.x >> 3;
+    const size_t base = AXIS == 1 ? ((size_t)o << 16 | r) : ((size_t)o << 8 | r);
+    const size_t stride = AXIS == 1 ? 256 : 65536;
+    uint32_t *p = lut + base + (size_t)(32 * w) * stride;
+    uint32_t k[32], m[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) k[j] = p[(size_t)j * stride];
+    m[0] = k[0];
+#pragma unroll
+    for (int j = 1; j < 32; j++) m[j] = min(k[j], idx_step(m[j - 1], 1));
+    carry[0][w][lane] = m[31];  // local forward value at the segment's last position
+    uint32_t run = k[31];
+#pragma unroll
+    for (int j = 30; j >= 0; j--) {
+        run = min(k[j], idx_step(run, 1));
+        m[j] = min(m[j], run);
+    }
+    carry[1][w][lane] = run;    // local backward value at the segment's first position
+    __syncthreads();
+    uint32_t cf = IDX_EMPTY, cb = IDX_EMPTY;  // carries as seen at my position 0 (forward) / 31 (backward)
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        if ((uint32_t)v < w) cf = min(cf, idx_step(carry[0][v][lane], 32 * (w - v) - 31));
+        if ((uint32_t)v > w) cb = min(cb, idx_step(carry[1][v][lane], 32 * (v - w) - 31));
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) p[(size_t)j * stride] = min(m[j], min(idx_step(cf, j), idx_step(cb, 31 - j)));
+}
+
 // ---------------------------------------------------------------------------------------
 // compact form: u16 slot per cell
 // ---------------------------------------------------------------------------------------
@@ -201,10 +240,18 @@ int emo_launch_build_index(emo_ctx *ctx) {
     EMO_LAUNCH_CHECK(ctx);
     // (keeping the forward sweep in shared memory instead of in place — one read and one write of the table per axis instead of
     // two — was measured: 32 KB per warp leaves 6 warps per SM and the axis takes ~55 us instead of 36)
-    index_sweep_kernel<1><<<256, 256, 0, ctx->stream>>>(ctx->lut);
-    EMO_LAUNCH_CHECK(ctx);
-    index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
-    EMO_LAUNCH_CHECK(ctx);
+    static const bool sweep_old = getenv("EMO_INDEX_SWEEP") && atoi(getenv("EMO_INDEX_SWEEP")) == 0;  // A-B switch: the in-place sweeps
+    if (sweep_old) {
+        index_sweep_kernel<1><<<256, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+    } else {
+        index_sweep_reg_kernel<1><<<2048, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        index_sweep_reg_kernel<2><<<2048, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+    }
     ctx->lut_valid = true;
     // the compact form
     ctx->lut16_mode = 0;
