@@ -84,6 +84,7 @@ struct emo_ctx {
     bool has_px = false;
     uint32_t *lut = nullptr;  // 1to1 search index: [256 b][256 g][256 r] keys dist << 22 | tile (index.cu), 64 MiB
     bool lut_valid = false;   // built for the resident library
+    uint32_t *idx_seeded = nullptr;  // one bit per cell: a library colour lives here (2 MiB; index.cu, build only)
     uint16_t *lut16 = nullptr;  // compact form: slot of the winner per cell, 32 MiB (index.cu)
     int lut16_mode = 0;         // 0: none, 1: slot = tile index (T <= 65 536), 2: slot -> idx_entry {tile, colour}, 3: 2 pending the winner count
     uint32_t lut16_slots = 0;

@@ -76,6 +76,7 @@ void emo_destroy(emo_ctx *ctx) {
     cudaFree(ctx->lib_px);
     cudaFree(ctx->lut);
     cudaFree(ctx->lut16);
+    cudaFree(ctx->idx_seeded);
     cudaFree(ctx->idx_slot_of_tile);
     cudaFree(ctx->idx_entry);
     if (ctx->idx_count_host) cudaFreeHost((void *)ctx->idx_count_host);

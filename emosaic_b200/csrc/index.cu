@@ -49,15 +49,47 @@ __global__ void index_seed_kernel(const uint32_t *__restrict__ cand, uint32_t T,
     if (t < T) atomicMin(&lut[cand[t] & 0xFFFFFFu], t);
 }
 
+// The same without clearing the 64 MiB table first: a bit per cell says "a library colour lives here" (2 MiB, cleared per build),
+// the marked cells are reset by this kernel, index_seed_kernel then takes the minimum over them, and the r pass reads nothing but
+// the bits and the marked cells and writes every line from scratch.
+__global__ void index_mark_kernel(const uint32_t *__restrict__ cand, uint32_t T, uint32_t *__restrict__ seeded, uint32_t *__restrict__ lut) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const uint32_t c = cand[t] & 0xFFFFFFu;
+    atomicOr(&seeded[c >> 5], 1u << (c & 31));
+    lut[c] = IDX_EMPTY;  // every writer of a cell stores the same value
+}
+
 // Pass along r (the contiguous axis): one warp per 256-cell line, 8 consecutive cells per lane (two
 // LDG.128 / STG.128), prefix- and suffix-min across lanes by shuffle.  Offsetting a lane's boundary
 // key by its distance to the far end of the line turns "min of key + distance" into a plain min-scan.
-__global__ void __launch_bounds__(256) index_sweep_r_kernel(uint32_t *__restrict__ lut) {
+// SPARSE: the table holds valid keys only where `seeded` has a bit (index_mark_kernel); everything else counts as empty.
+template <bool SPARSE>
+__global__ void __launch_bounds__(256) index_sweep_r_kernel(uint32_t *__restrict__ lut, const uint32_t *__restrict__ seeded) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // g | b << 8
     uint4 *p = reinterpret_cast<uint4 *>(lut + ((size_t)line << 8)) + lane * 2;
-    const uint4 a = p[0], b = p[1];
-    uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t k[8];
+    if (SPARSE) {
+        const uint32_t bits = (__ldg(seeded + line * 8 + (lane >> 2)) >> (8 * (lane & 3))) & 0xFFu;  // my 8 cells
+#pragma unroll
+        for (int m = 0; m < 8; m++) k[m] = IDX_EMPTY;
+        if (__ballot_sync(0xFFFFFFFFu, bits != 0) == 0) {  // no library colour on this line (most lines of a clustered library)
+            p[0] = make_uint4(IDX_EMPTY, IDX_EMPTY, IDX_EMPTY, IDX_EMPTY);
+            p[1] = make_uint4(IDX_EMPTY, IDX_EMPTY, IDX_EMPTY, IDX_EMPTY);
+            return;
+        }
+        if (bits) {
+            const uint4 a = p[0], b = p[1];
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                if (bits >> m & 1) k[m] = v[m];
+        }
+    } else {
+        const uint4 a = p[0], b = p[1];
+        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    }
     uint32_t f[8], s[8];
     // inside the lane
     f[0] = k[0];
@@ -163,6 +195,53 @@ __global__ void __launch_bounds__(256) index_sweep_reg_kernel(uint32_t *__restri
     for (int j = 0; j < 32; j++) p[(size_t)j * stride] = min(m[j], min(idx_step(cf, j), idx_step(cb, 31 - j)));
 }
 
+// The b pass with the compact form written on the way out (MODE 1: slot = tile index, MODE 2: slot_of_tile).  Same sweep as
+// index_sweep_reg_kernel<2>, but a warp spans 8 r x 4 g (four 32-byte sectors per access) so that four consecutive b of a thread
+// complete whole 4 x 4 x 4 blocks of the compact layout inside the warp: the 16 lanes of an r-block write one 32-byte run of the
+// block's 128-byte line per b.  Saves the compaction pass (a second read of the 64 MiB table and a launch).
+__host__ __device__ __forceinline__ uint32_t idx16_pos(uint32_t c);
+template <int MODE>
+__global__ void __launch_bounds__(256) index_sweep_b_compact_kernel(uint32_t *__restrict__ lut, const uint32_t *__restrict__ slot_of_tile,
+                                                                    uint16_t *__restrict__ lut16) {
+    __shared__ uint32_t carry[2][8][32];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t r = (blockIdx.x & 31) * 8 + (lane & 7), g = (blockIdx.x >> 5) * 4 + (lane >> 3);
+    const uint32_t cell0 = (32 * w) << 16 | g << 8 | r;  // position 0 of my segment
+    uint32_t *p = lut + cell0;
+    const size_t stride = 65536;
+    uint32_t k[32], m[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) k[j] = p[(size_t)j * stride];
+    m[0] = k[0];
+#pragma unroll
+    for (int j = 1; j < 32; j++) m[j] = min(k[j], idx_step(m[j - 1], 1));
+    carry[0][w][lane] = m[31];
+    uint32_t run = k[31];
+#pragma unroll
+    for (int j = 30; j >= 0; j--) {
+        run = min(k[j], idx_step(run, 1));
+        m[j] = min(m[j], run);
+    }
+    carry[1][w][lane] = run;
+    __syncthreads();
+    uint32_t cf = IDX_EMPTY, cb = IDX_EMPTY;
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        if ((uint32_t)v < w) cf = min(cf, idx_step(carry[0][v][lane], 32 * (w - v) - 31));
+        if ((uint32_t)v > w) cb = min(cb, idx_step(carry[1][v][lane], 32 * (v - w) - 31));
+    }
+    // position of (r, g, b = 32w) in the compact table; b + 1 is 16 entries further inside a block, b + 4 the next block along b
+    const uint32_t pos0 = idx16_pos(cell0);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t key = min(m[j], min(idx_step(cf, j), idx_step(cb, 31 - j)));
+        p[(size_t)j * stride] = key;
+        uint32_t slot = key & IDX_TILE_MASK;
+        if (MODE == 2) slot = __ldg(slot_of_tile + slot);
+        lut16[pos0 + ((uint32_t)(j >> 2) << 18) + ((uint32_t)(j & 3) << 4)] = (uint16_t)slot;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // compact form: u16 slot per cell
 // ---------------------------------------------------------------------------------------
@@ -223,6 +302,7 @@ __global__ void __launch_bounds__(256) index_compact_kernel(const uint32_t *__re
 int emo_index_reserve(emo_ctx *ctx) {
     if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
     if (!ctx->lut16) EMO_CK(cudaMalloc(&ctx->lut16, IDX_CELLS * sizeof(uint16_t)));
+    if (!ctx->idx_seeded) EMO_CK(cudaMalloc(&ctx->idx_seeded, IDX_CELLS / 8));
     if (ctx->T > IDX16_SLOTS) {
         int rc = emo_ensure(ctx, (void **)&ctx->idx_slot_of_tile, &ctx->idx_slot_cap, (size_t)ctx->T * 4);
         if (rc) return rc;
@@ -231,41 +311,8 @@ int emo_index_reserve(emo_ctx *ctx) {
     return EMO_OK;
 }
 
-int emo_launch_build_index(emo_ctx *ctx) {
-    if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
-    EMO_CK(cudaMemsetAsync(ctx->lut, 0xFF, IDX_CELLS * sizeof(uint32_t), ctx->stream));
-    index_seed_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->lut);
-    EMO_LAUNCH_CHECK(ctx);
-    index_sweep_r_kernel<<<65536 / 8, 256, 0, ctx->stream>>>(ctx->lut);
-    EMO_LAUNCH_CHECK(ctx);
-    // (keeping the forward sweep in shared memory instead of in place — one read and one write of the table per axis instead of
-    // two — was measured: 32 KB per warp leaves 6 warps per SM and the axis takes ~55 us instead of 36)
-    static const bool sweep_old = getenv("EMO_INDEX_SWEEP") && atoi(getenv("EMO_INDEX_SWEEP")) == 0;  // A-B switch: the in-place sweeps
-    if (sweep_old) {
-        index_sweep_kernel<1><<<256, 256, 0, ctx->stream>>>(ctx->lut);
-        EMO_LAUNCH_CHECK(ctx);
-        index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
-        EMO_LAUNCH_CHECK(ctx);
-    } else {
-        index_sweep_reg_kernel<1><<<2048, 256, 0, ctx->stream>>>(ctx->lut);
-        EMO_LAUNCH_CHECK(ctx);
-        index_sweep_reg_kernel<2><<<2048, 256, 0, ctx->stream>>>(ctx->lut);
-        EMO_LAUNCH_CHECK(ctx);
-    }
-    ctx->lut_valid = true;
-    // the compact form
-    ctx->lut16_mode = 0;
-    static const bool wide_only = getenv("EMO_INDEX_WIDE") && atoi(getenv("EMO_INDEX_WIDE")) != 0;  // tests / tuning: u32 table only
-    if (wide_only) return EMO_OK;
-    if (!ctx->lut16) EMO_CK(cudaMalloc(&ctx->lut16, IDX_CELLS * sizeof(uint16_t)));
-    if (ctx->T <= IDX16_SLOTS) {
-        index_compact_kernel<true><<<(uint32_t)(IDX_CELLS / 64 / 256), 256, 0, ctx->stream>>>(ctx->lut, nullptr, ctx->lut16);
-        EMO_LAUNCH_CHECK(ctx);
-        ctx->lut16_slots = ctx->T;
-        ctx->lut16_mode = 1;  // slot = tile index, colours = the candidate array
-        return EMO_OK;
-    }
-    // larger libraries: distinct winners, if there are at most 65 536 of them
+// winner bookkeeping of libraries above 65 536 tiles: slots for the distinct winners, the count on its way to the host
+static int index_launch_winners(emo_ctx *ctx) {
     int rc;
     if ((rc = emo_ensure(ctx, (void **)&ctx->idx_slot_of_tile, &ctx->idx_slot_cap, (size_t)ctx->T * 4))) return rc;
     if (!ctx->idx_entry) EMO_CK(cudaMalloc(&ctx->idx_entry, IDX16_SLOTS * sizeof(uint2) + 16));
@@ -283,9 +330,74 @@ int emo_launch_build_index(emo_ctx *ctx) {
     }
     EMO_CK(cudaMemcpyAsync((void *)ctx->idx_count_host, counter, 4, cudaMemcpyDeviceToHost, ctx->stream));
     EMO_CK(cudaEventRecord(ctx->idx_count_ev, ctx->stream));
-    index_compact_kernel<false><<<(uint32_t)(IDX_CELLS / 64 / 256), 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_slot_of_tile, ctx->lut16);
-    EMO_LAUNCH_CHECK(ctx);
-    ctx->lut16_mode = 3;  // slot -> {tile, colour} entries, pending the winner count (resolved to 2 or 0 by index16_resolve)
+    return EMO_OK;
+}
+
+int emo_launch_build_index(emo_ctx *ctx) {
+    if (!ctx->lut) EMO_CK(cudaMalloc(&ctx->lut, IDX_CELLS * sizeof(uint32_t)));
+    static const bool wide_only = getenv("EMO_INDEX_WIDE") && atoi(getenv("EMO_INDEX_WIDE")) != 0;  // tests / tuning: u32 table only
+    static const bool sweep_old = getenv("EMO_INDEX_SWEEP") && atoi(getenv("EMO_INDEX_SWEEP")) == 0;  // A-B switch: the first build
+    const bool direct = ctx->T <= IDX16_SLOTS;  // slot = tile index, colours = the candidate array
+    int rc;
+    ctx->lut16_mode = 0;
+    if (!wide_only && !ctx->lut16) EMO_CK(cudaMalloc(&ctx->lut16, IDX_CELLS * sizeof(uint16_t)));
+    if (sweep_old) {
+        // memset + seeds + in-place sweeps (two reads and two writes of the table per strided axis) + a separate compaction pass
+        EMO_CK(cudaMemsetAsync(ctx->lut, 0xFF, IDX_CELLS * sizeof(uint32_t), ctx->stream));
+        index_seed_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        index_sweep_r_kernel<false><<<65536 / 8, 256, 0, ctx->stream>>>(ctx->lut, nullptr);
+        EMO_LAUNCH_CHECK(ctx);
+        index_sweep_kernel<1><<<256, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        index_sweep_kernel<2><<<256, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        ctx->lut_valid = true;
+        if (wide_only) return EMO_OK;
+        if (direct) {
+            index_compact_kernel<true><<<(uint32_t)(IDX_CELLS / 64 / 256), 256, 0, ctx->stream>>>(ctx->lut, nullptr, ctx->lut16);
+            EMO_LAUNCH_CHECK(ctx);
+        } else {
+            if ((rc = index_launch_winners(ctx))) return rc;
+            index_compact_kernel<false><<<(uint32_t)(IDX_CELLS / 64 / 256), 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_slot_of_tile, ctx->lut16);
+            EMO_LAUNCH_CHECK(ctx);
+        }
+    } else {
+        // Seeds without clearing the table (a bit per cell), the r pass writes every line from scratch, the strided passes keep
+        // their lines in registers, the last one writes the compact form on its way out.  (keeping the forward sweep of a strided
+        // axis in shared memory was measured in round 2: 32 KB per warp leaves 6 warps per SM, ~55 us per axis)
+        // (marking costs two passes over the tiles: above ~0.5 M tiles clearing the whole table is cheaper again)
+        const bool sparse = ctx->T <= 500000;
+        if (sparse) {
+            if (!ctx->idx_seeded) EMO_CK(cudaMalloc(&ctx->idx_seeded, IDX_CELLS / 8));
+            EMO_CK(cudaMemsetAsync(ctx->idx_seeded, 0, IDX_CELLS / 8, ctx->stream));
+            index_mark_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->idx_seeded, ctx->lut);
+            EMO_LAUNCH_CHECK(ctx);
+        } else {
+            EMO_CK(cudaMemsetAsync(ctx->lut, 0xFF, IDX_CELLS * sizeof(uint32_t), ctx->stream));
+        }
+        index_seed_kernel<<<(ctx->T + 255) / 256, 256, 0, ctx->stream>>>(ctx->cand, ctx->T, ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        // a tile wins somewhere iff it owns its own colour cell, and the sweeps never change a seeded cell: the winners are known now
+        if (!wide_only && !direct && (rc = index_launch_winners(ctx))) return rc;
+        if (sparse) index_sweep_r_kernel<true><<<65536 / 8, 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_seeded);
+        else index_sweep_r_kernel<false><<<65536 / 8, 256, 0, ctx->stream>>>(ctx->lut, nullptr);
+        EMO_LAUNCH_CHECK(ctx);
+        index_sweep_reg_kernel<1><<<2048, 256, 0, ctx->stream>>>(ctx->lut);
+        EMO_LAUNCH_CHECK(ctx);
+        if (wide_only) index_sweep_reg_kernel<2><<<2048, 256, 0, ctx->stream>>>(ctx->lut);
+        else if (direct) index_sweep_b_compact_kernel<1><<<2048, 256, 0, ctx->stream>>>(ctx->lut, nullptr, ctx->lut16);
+        else index_sweep_b_compact_kernel<2><<<2048, 256, 0, ctx->stream>>>(ctx->lut, ctx->idx_slot_of_tile, ctx->lut16);
+        EMO_LAUNCH_CHECK(ctx);
+        ctx->lut_valid = true;
+        if (wide_only) return EMO_OK;
+    }
+    if (direct) {
+        ctx->lut16_slots = ctx->T;
+        ctx->lut16_mode = 1;
+    } else {
+        ctx->lut16_mode = 3;  // slot -> {tile, colour} entries, pending the winner count (resolved to 2 or 0 by index16_resolve)
+    }
     return EMO_OK;
 }
 
