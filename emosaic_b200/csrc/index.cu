@@ -63,6 +63,13 @@ __global__ void index_mark_kernel(const uint32_t *__restrict__ cand, uint32_t T,
 // Pass along r (the contiguous axis): one warp per 256-cell line, 8 consecutive cells per lane (two
 // LDG.128 / STG.128), prefix- and suffix-min across lanes by shuffle.  Offsetting a lane's boundary
 // key by its distance to the far end of the line turns "min of key + distance" into a plain min-scan.
+// one 32-byte sector per lane in a single instruction (sm_100: 256-bit global stores)
+__device__ __forceinline__ void stg_v8(uint32_t *p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 // SPARSE: the table holds valid keys only where `seeded` has a bit (index_mark_kernel); everything else counts as empty.
 template <bool SPARSE>
 __global__ void __launch_bounds__(256) index_sweep_r_kernel(uint32_t *__restrict__ lut, const uint32_t *__restrict__ seeded) {
@@ -75,8 +82,7 @@ __global__ void __launch_bounds__(256) index_sweep_r_kernel(uint32_t *__restrict
 #pragma unroll
         for (int m = 0; m < 8; m++) k[m] = IDX_EMPTY;
         if (__ballot_sync(0xFFFFFFFFu, bits != 0) == 0) {  // no library colour on this line (most lines of a clustered library)
-            p[0] = make_uint4(IDX_EMPTY, IDX_EMPTY, IDX_EMPTY, IDX_EMPTY);
-            p[1] = make_uint4(IDX_EMPTY, IDX_EMPTY, IDX_EMPTY, IDX_EMPTY);
+            stg_v8(reinterpret_cast<uint32_t *>(p), k);
             return;
         }
         if (bits) {
@@ -117,8 +123,7 @@ __global__ void __launch_bounds__(256) index_sweep_r_kernel(uint32_t *__restrict
     uint32_t o[8];
 #pragma unroll
     for (int m = 0; m < 8; m++) o[m] = min(min(f[m], s[m]), min(idx_step(cf, m), idx_step(cb, 7 - m)));
-    p[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    p[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    stg_v8(reinterpret_cast<uint32_t *>(p), o);
 }
 
 // Pass along g (stride 256 cells) or b (stride 65 536 cells): one thread per line, neighbouring threads on
