@@ -18,7 +18,8 @@
 //
 // Data layout in HBM: candidates packed [Lpad][WORDS] u32 (WORDS = ceil(3N/4), bytes of the
 // 3N-vector little-endian, zero padded), padded to a multiple of the stage size with copies of
-// the last real candidate (a duplicate of an earlier candidate can never win under strict `<`).
+// the last real candidate (a duplicate of an earlier candidate can never win under strict `<`); the last
+// stage is scanned up to the last whole window that holds a real candidate, the rest of the padding is only there to be loadable.
 // A CTA keeps NT*R queries in registers and streams the whole candidate array through a
 // 4-stage shared-memory ring filled by TMA bulk copies issued from a dedicated producer warp;
 // every candidate word is read with a warp-broadcast LDS.128 and reused for R queries.

@@ -16,7 +16,10 @@
 // exactly as f32::sin does in the reference) are computed on the host in resize_axis() and cached per geometry; all
 // O(pixels) arithmetic runs here.
 //
-//   resize_vertical_kernel<ALIGNED, TRANSPOSED>: one thread per (image, output row, 8 consecutive bytes of the view row).
+//   resize_vertical2_kernel<TRANSPOSED, DEPTH, NB>: the vertical pass of every 8-byte aligned geometry — two output rows per
+//     thread share the loads and the byte -> 2^23 + b step where their windows overlap (see the kernel).
+//   resize_vertical_kernel<ALIGNED, TRANSPOSED>: one thread per (image, output row, 8 consecutive bytes of the view row); the
+//     path of rows that are not 8-byte aligned and of tap tables whose neighbouring windows are not monotone.
 //     Rows of the view are read as one 64-bit word when the geometry keeps them 8-byte aligned, else as the two or three
 //     covering aligned 32-bit words funnel-shifted by the row's phase.  The product f32(b) * w of a tap is formed WITHOUT
 //     converting the byte first: PRMT builds x = 0x4B0000bb = 2^23 + b (exact), and fma(x, w, -2^23 * w) =
@@ -32,10 +35,10 @@
 //     every tap as one coalesced 128-byte row of the transposed image (the row-major layout costs 32 cache lines per load).
 //   resize_horizontal_kernel: one thread per (image, row, output pixel), lanes along the output row, weights stored
 //     tap-major ([tap][ox]) so that lanes read consecutive words.
-//   resize_horizontal_smem_kernel: row-major input whose output pixels are 4+ source pixels apart (a single photo, batches
-//     of very small tiles): the tmp row is staged into shared memory with coalesced loads (skewed by one word per 32 so
-//     that lanes 3*ratio floats apart hit different banks) and each thread runs its tap chain from there — the global
-//     version of this access pattern costs 32 cache lines per load.
+//   resize_horizontal_smem_kernel<WS>: row-major input whose output pixels are 4+ source pixels apart (a single photo,
+//     batches of very small tiles): the tmp row is staged into shared memory with coalesced loads (skewed by one word per 32
+//     so that lanes 3*ratio floats apart hit different banks) and each thread runs its tap chain from there — the global
+//     version of this access pattern costs 32 cache lines per load.  WS: fewer blocks than SMs, the weights are staged too.
 //   resize_horizontal_t_kernel: transposed input, one block per (image, output column), lanes along oy, weights uniform.
 //   resize_copy_kernel: the "(nwidth, nheight) == image.dimensions()" early return of resize() — a plain copy.
 #include <math.h>
