@@ -178,3 +178,18 @@ def test_library_tap_tables_equal_the_oracle(n_in, n_out):
     ol, oc, ow = oracle.resize_axis(n_in, n_out)
     assert (left == ol).all() and (cnt == oc).all() and ws.shape == ow.shape
     assert (ws.view(np.uint32) == ow.view(np.uint32)).all()
+
+
+def test_tap_windows_of_neighbouring_outputs_are_monotone():
+    """resize_vertical2_kernel (resize.cu) gives two neighbouring output rows to one thread and walks the union of their windows
+    once; that needs left[o] <= left[o + 1] and left[o] + cnt[o] <= left[o + 1] + cnt[o + 1] (the launcher checks it per geometry
+    and falls back to one row per thread otherwise).  The windows are floor / ceil of monotone functions of o clamped to the
+    axis, so this must hold for every geometry: shrink, stretch, near-identity, one-pixel axes."""
+    rng = np.random.default_rng(12)
+    geoms = [(4097, 4096), (8192, 4096), (3000, 64), (2048, 64), (256, 8), (7, 31), (1, 5), (300, 1), (1024, 4096), (64, 64), (65535, 3)]
+    geoms += [(int(a), int(b)) for a, b in zip(rng.integers(1, 5000, 60), rng.integers(1, 3000, 60))]
+    for n_in, n_out in geoms:
+        left, cnt, _ = api.resize_taps(n_in, n_out)
+        end = left.astype(np.int64) + cnt
+        assert (np.diff(left.astype(np.int64)) >= 0).all() and (np.diff(end) >= 0).all(), (n_in, n_out)
+        assert (cnt >= 1).all() and (end <= n_in).all()
